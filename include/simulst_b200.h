@@ -1,0 +1,237 @@
+/*
+ * simulst_b200 -- C ABI of the B200 (sm_100a) streaming-alignment hot path.
+ *
+ * Drop-in boundary for the tensor math of George0828Zhang/simulst (reference paths are
+ * relative to its repository root).  The reference reaches this math through plain Python
+ * functions; a maintainer binds the entry points below with ctypes (see INTEGRATION.md and
+ * simulst_b200/_lib.py).  Everything is `extern "C"`, plain pointers and sizes.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers on the current CUDA device unless noted; tensors are
+ *    dense row-major ("contiguous").  The caller allocates every input, output and
+ *    workspace; the library never allocates or frees device memory and keeps no pointer
+ *    after a call returns.
+ *  - All work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default
+ *    stream).  No hidden synchronisation, no host reads: every call is CUDA-graph capturable.
+ *  - Return value: 0 on success, a negative SIMULST_E_* code on argument / launch errors
+ *    (checked on the host, synchronously).  No C++ exception crosses the ABI.
+ *  - Data errors (NaN or out-of-range probabilities: the reference's `prob_check` /
+ *    `safe_cumprod` assertions, codebase/utils/functions.py:9-17,57-61) are OR-ed by the
+ *    kernels into the caller-provided device word `status` (may be NULL = don't record).
+ *    The host wrapper decides when to look at it (strict: right away; default: lazily).
+ *  - dtype enums select the element type of activation tensors; accumulation is always fp32.
+ */
+#ifndef SIMULST_B200_H_
+#define SIMULST_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIMULST_VERSION 100 /* 0.1.0 */
+
+/* element types */
+#define SIMULST_F32 0
+#define SIMULST_BF16 1
+#define SIMULST_F16 2
+
+/* error codes */
+#define SIMULST_OK 0
+#define SIMULST_E_ARG (-1)        /* null pointer / bad enum / bad flag combination */
+#define SIMULST_E_SHAPE (-2)      /* dimension <= 0 or beyond the supported maximum */
+#define SIMULST_E_ARCH (-3)       /* device is not sm_100 */
+#define SIMULST_E_LAUNCH (-4)     /* cudaGetLastError() after launch */
+#define SIMULST_E_ALIGN (-5)      /* pointer not aligned for its element type */
+
+/* bits OR-ed into the device status word */
+#define SIMULST_ST_NAN 1u         /* "Nan in a probability tensor."                    */
+#define SIMULST_ST_RANGE 2u       /* "Incorrect values in a probability tensor"        */
+#define SIMULST_ST_NEGPROD 4u     /* safe_cumprod: input + eps < 0                     */
+
+/* flags of the MMA entry points */
+#define SIMULST_MMA_MASS_PRESERVATION 1u /* apply mass_preservation to the alpha output  */
+#define SIMULST_MMA_SOFT 2u              /* also produce beta (expected soft attention)  */
+#define SIMULST_MMA_ENERGY_F16_FILL 4u   /* masked energy fill is -1e4 (fp16 energies)
+                                            instead of -1e8 (monotonic_attention.py:106) */
+#define SIMULST_MMA_LEFT_PADDING 8u      /* mass_preservation(left_padding=True)         */
+
+#define SIMULST_MMA_MAX_SRC 16384        /* longest source row a single CTA keeps on chip */
+
+int simulst_version(void);
+const char* simulst_error_string(int code);
+
+/* Number of kernels this library has launched since it was loaded / since the last reset
+ * (host-side counter; used by bench.py for its `gpu_launches` claim). */
+long long simulst_launch_count(void);
+void simulst_reset_launch_count(void);
+
+/* Tuning override for the MMA training kernels: threads per CTA and elements per thread
+ * (threads * vpt >= S required).  0,0 restores automatic selection.  Returns 0 or E_ARG. */
+int simulst_mma_set_config(int threads, int vpt);
+/* 1 = stage rows with TMA bulk copies when alignment allows (default), 0 = cooperative loads */
+int simulst_mma_set_tma(int enable);
+
+/* ---------------------------------------------------------------------------------------
+ * MMA training path, forward.   Replaces, fused in one launch,
+ *   expected_alignment_from_p_choose   codebase/utils/monotonic_attention.py:12-76
+ *   mass_preservation                  codebase/utils/monotonic_attention.py:155-197
+ *   expected_soft_attention            codebase/utils/monotonic_attention.py:79-152
+ * i.e. steps 2-3 of MonotonicAttention.monotonic_attention_process_train
+ * (codebase/modules/monotonic_multihead_attention.py:318-347).
+ *
+ *   p_choose      [N,T,S] p_dtype   stepwise probabilities (N = batch * heads)
+ *   soft_energy   [N,T,S] e_dtype   soft-attention energies; NULL unless SIMULST_MMA_SOFT
+ *   padding_mask  [N,S]   uint8     non-zero = padded source position; NULL = no padding
+ *   alpha         [N,T,S] fp32 out  expected alignment (mass-preserved if the flag is set)
+ *   beta          [N,T,S] fp32 out  expected soft attention; NULL unless SIMULST_MMA_SOFT
+ *   side          [N,T,2] fp32 out  saved for backward when MASS_PRESERVATION is set:
+ *                                   {alpha value overwritten by the residual, row sum};
+ *                                   may be NULL when no backward will follow
+ *   chunk_size    0 = infinite lookback, c >= 1 = chunkwise window (moving_sum)
+ */
+int simulst_mma_train_fwd(const void* p_choose, int p_dtype,
+                          const void* soft_energy, int e_dtype,
+                          const uint8_t* padding_mask,
+                          float* alpha, float* beta, float* side,
+                          int N, int T, int S,
+                          float eps, int chunk_size, unsigned flags,
+                          unsigned* status, void* stream);
+
+/* MMA training path, backward (scans recomputed from p_choose / soft_energy; the only saved
+ * tensors are the forward outputs).  Autograd of the three functions above.
+ *   alpha, side     forward outputs
+ *   grad_alpha      [N,T,S] fp32  dL/d(alpha output) or NULL (= 0)
+ *   grad_beta       [N,T,S] fp32  dL/d(beta) or NULL (= 0; must be NULL without SOFT)
+ *   grad_p          [N,T,S] gp_dtype out
+ *   grad_energy     [N,T,S] ge_dtype out (NULL without SOFT)
+ */
+int simulst_mma_train_bwd(const void* p_choose, int p_dtype,
+                          const void* soft_energy, int e_dtype,
+                          const uint8_t* padding_mask,
+                          const float* alpha, const float* side,
+                          const float* grad_alpha, const float* grad_beta,
+                          void* grad_p, int gp_dtype, void* grad_energy, int ge_dtype,
+                          int N, int T, int S,
+                          float eps, int chunk_size, unsigned flags,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Stand-alone pieces (same math, rows independent): used when the reference functions are
+ * called one by one rather than through monotonic_attention_process_train.
+ */
+
+/* expected_soft_attention(alpha, soft_energy, padding_mask, chunk_size, eps)
+ * (monotonic_attention.py:79-152).  a_dtype is the dtype of alpha AND of the beta output. */
+int simulst_soft_attention_fwd(const void* alpha, int a_dtype,
+                               const void* soft_energy, int e_dtype,
+                               const uint8_t* padding_mask, void* beta,
+                               int N, int T, int S, float eps, int chunk_size, unsigned flags,
+                               unsigned* status, void* stream);
+int simulst_soft_attention_bwd(const void* alpha, int a_dtype,
+                               const void* soft_energy, int e_dtype,
+                               const uint8_t* padding_mask, const void* grad_beta,
+                               void* grad_alpha, void* grad_energy,
+                               int N, int T, int S, float eps, int chunk_size, unsigned flags,
+                               void* stream);
+
+/* mass_preservation(alpha, padding_mask, left_padding) (monotonic_attention.py:155-197).
+ * In place on `alpha` [N,T,S] fp32; writes side [N,T,2] like the fused forward. */
+int simulst_mass_preservation_fwd(float* alpha, const uint8_t* padding_mask, float* side,
+                                  int N, int T, int S, unsigned flags,
+                                  unsigned* status, void* stream);
+/* grad_in [N,T,S] fp32 (dL/d output) -> grad_out [N,T,S] fp32 (dL/d input); may alias. */
+int simulst_mass_preservation_bwd(const float* grad_in, const uint8_t* padding_mask,
+                                  const float* side, float* grad_out,
+                                  int N, int T, int S, unsigned flags, void* stream);
+
+/* moving_sum(x, start_idx, end_idx) (codebase/utils/functions.py:69-125):
+ * out[n] = sum_{m = n-start+1}^{n+end-1} x[m] along the last axis, zero outside. rows = N*T. */
+int simulst_moving_sum(const void* x, void* out, int dtype, long long rows, int S,
+                       int start_idx, int end_idx, void* stream);
+
+/* exclusive_cumprod(x, dim=last, eps) = exp(cumsum(log(cat[1, x] + eps)))[:-1]
+ * (functions.py:20-66). */
+int simulst_exclusive_cumprod(const void* x, void* out, int dtype, long long rows, int S,
+                              float eps, unsigned* status, void* stream);
+
+/* learnable_p_choose (codebase/utils/p_choose_strategy.py:56-76):
+ * out = sigmoid(energy + noise), noise may be NULL (eval).  Same dtype in and out; the
+ * Gaussian noise is drawn by the caller (torch RNG) so that results are reproducible. */
+int simulst_p_choose(const void* energy, const void* noise, void* out, int dtype,
+                     long long numel, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * MMA incremental decoding step.  Replaces the body of
+ * MonotonicAttention.monotonic_attention_process_infer
+ * (codebase/modules/monotonic_multihead_attention.py:171-299) after the energy bmm's.
+ *
+ *   p_choose     [R,S] p_dtype      sigmoid(monotonic energy) for this step (R = bsz*heads)
+ *   soft_energy  [R,S] e_dtype      NULL for hard-aligned attention
+ *   src_lengths  [R] int32          valid source length per row; NULL = S for all rows
+ *   head_step    [R] int64 in/out   the `head_step` cache (zeros before the first step)
+ *   head_read    [R] uint8 out      the `head_read` cache (bool)
+ *   alpha        [R,S] o_dtype out  one-hot alignment
+ *   beta         [R,S] o_dtype out  softmax over the look-back window; NULL for hard
+ */
+int simulst_mma_step(const void* p_choose, int p_dtype,
+                     const void* soft_energy, int e_dtype,
+                     const int32_t* src_lengths,
+                     int64_t* head_step, uint8_t* head_read,
+                     void* alpha, void* beta, int o_dtype,
+                     int R, int S, unsigned flags, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * CIF (continuous integrate-and-fire).  Replaces cif_function
+ * (codebase/models/torch_cif/cif.py:23-196) in three launches, with one optional host read
+ * (the output length T, exactly where the reference reads `feat_lengths.max()`).
+ *
+ * Pass 1, simulst_cif_plan: per batch row, scale alpha (training mode), inclusive-scan it,
+ * and derive the firing indices.
+ *   alpha        [B,S] a_dtype      integration weights (after sigmoid)
+ *   padding_mask [B,S] uint8        or NULL
+ *   desired_sum  [B] fp32           training mode: beta*target_length+eps as computed by the
+ *                                   host wrapper in the input dtype (cif.py:68); NULL = inference
+ *   target_lengths [B] int64        training mode lengths; NULL = inference
+ *   csum         [B,S] fp32 out     cumsum of the (scaled) weights
+ *   alpha_sum    [B] fp32 out       sum of the unscaled masked weights (cif.py:69,74)
+ *   lengths      [B] int64 out      feat_lengths before tail handling
+ *   t_max        [1] int32 out      max over rows of `lengths` (atomicMax; zero it first)
+ */
+int simulst_cif_plan(const void* alpha, int a_dtype, const uint8_t* padding_mask,
+                     const float* desired_sum, const int64_t* target_lengths,
+                     float* csum, float* scale, float* alpha_sum, int64_t* lengths,
+                     int* t_max, int B, int S, float beta, unsigned* status, void* stream);
+
+/* Pass 2, simulst_cif_fwd: weighted segment sums (gather formulation: every output slot
+ * reads one contiguous source range, deterministic, no atomics) plus tail handling.
+ *   input        [B,S,C] x_dtype
+ *   T            number of output slots BEFORE tail extension (= *t_max)
+ *   T_alloc      rows allocated in cif_out / delays (T in training mode, T+1 in inference)
+ *   cif_out      [B,T_alloc,C] x_dtype out
+ *   delays       [B,T_alloc] x_dtype out
+ *   tail_weights [B] fp32 out (inference only; NULL in training)
+ *   lengths      [B] int64 in/out (inference: += 1 where the tail fires)
+ *   bounds       [B,T_alloc+2] int32 workspace: first source frame of every output slot
+ */
+int simulst_cif_fwd(const void* input, int x_dtype, const float* csum, const float* scale,
+                    const void* alpha, int a_dtype, const uint8_t* padding_mask,
+                    void* cif_out, void* delays, float* tail_weights, int64_t* lengths,
+                    int* bounds, int B, int S, int C, int T, int T_alloc,
+                    float beta, float tail_thres, int training, void* stream);
+
+/* CIF backward: dL/d input and dL/d alpha given dL/d cif_out and dL/d delays. */
+int simulst_cif_bwd(const void* input, int x_dtype, const float* csum, const float* scale,
+                    const void* alpha, int a_dtype, const uint8_t* padding_mask,
+                    const void* grad_out, const void* grad_delays,
+                    const float* tail_weights, const int64_t* lengths_before_tail,
+                    const float* alpha_sum, const float* grad_alpha_sum,
+                    void* grad_input, void* grad_alpha, float* workspace,
+                    int B, int S, int C, int T, int T_alloc,
+                    float beta, float tail_thres, int training, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMULST_B200_H_ */

@@ -1,0 +1,154 @@
+// C-ABI entry points of the MMA training path (see include/simulst_b200.h).
+#include "mma_common.cuh"
+#include "mma_dispatch.h"
+
+namespace simulst {
+
+static int g_cfg_threads = 0, g_cfg_vpt = 0;   // 0 = automatic
+static int g_use_tma = 1;
+
+struct Config { int threads, vpt; };
+
+static bool config_exists(int threads, int vpt) {
+#define X(TH, VP) if (threads == TH && vpt == VP) return true;
+    SIMULST_MMA_CONFIGS(X)
+#undef X
+    return false;
+}
+
+// Smallest configuration that keeps a whole source row on chip.
+static Config pick_config(int S) {
+    if (g_cfg_threads > 0 && g_cfg_threads * g_cfg_vpt >= S) return {g_cfg_threads, g_cfg_vpt};
+    if (S <= 128) return {32, 4};
+    if (S <= 256) return {32, 8};
+    if (S <= 512) return {64, 8};
+    if (S <= 1024) return {128, 8};
+    if (S <= 2048) return {256, 8};
+    if (S <= 4096) return {512, 8};
+    if (S <= 6144) return {512, 12};
+    if (S <= 8192) return {512, 16};
+    return {1024, 16};
+}
+
+static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+static int check_device() {
+    static int cached[64] = {};     // 0 unknown, 1 ok, -1 wrong arch
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return SIMULST_E_ARCH;
+    int& c = cached[dev & 63];
+    if (c == 0) {
+        int major = 0;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        c = (major == 10) ? 1 : -1;
+    }
+    return c == 1 ? SIMULST_OK : SIMULST_E_ARCH;
+}
+
+static int mode_of(unsigned flags, int chunk) {
+    if (!(flags & SIMULST_MMA_SOFT)) return kModeHard;
+    return chunk > 0 ? kModeSoftCk : kModeSoftIL;
+}
+
+}  // namespace simulst
+
+using namespace simulst;
+
+extern "C" {
+
+int simulst_mma_set_config(int threads, int vpt) {
+    if (threads == 0 && vpt == 0) { g_cfg_threads = g_cfg_vpt = 0; return SIMULST_OK; }
+    if (!config_exists(threads, vpt)) return SIMULST_E_ARG;
+    g_cfg_threads = threads;
+    g_cfg_vpt = vpt;
+    return SIMULST_OK;
+}
+
+int simulst_mma_set_tma(int enable) {
+    g_use_tma = enable ? 1 : 0;
+    return SIMULST_OK;
+}
+
+int simulst_mma_train_fwd(const void* p_choose, int p_dtype, const void* soft_energy, int e_dtype,
+                          const uint8_t* padding_mask, float* alpha, float* beta, float* side,
+                          int N, int T, int S, float eps, int chunk_size, unsigned flags,
+                          unsigned* status, void* stream) {
+    const bool soft = (flags & SIMULST_MMA_SOFT) != 0u;
+    if (p_choose == nullptr || alpha == nullptr || !valid_dtype(p_dtype)) return SIMULST_E_ARG;
+    if (soft && (soft_energy == nullptr || beta == nullptr || e_dtype != p_dtype)) return SIMULST_E_ARG;
+    if (chunk_size < 0) return SIMULST_E_ARG;
+    if (N < 0 || T < 0 || S < 0 || S > SIMULST_MMA_MAX_SRC) return SIMULST_E_SHAPE;
+    if (N == 0 || T == 0 || S == 0) return SIMULST_OK;
+    const size_t esz = dtype_size(p_dtype);
+    if (!aligned(p_choose, esz) || (soft && !aligned(soft_energy, esz)) || !aligned(alpha, 4) ||
+        (soft && !aligned(beta, 4)))
+        return SIMULST_E_ALIGN;
+    int rc = check_device();
+    if (rc != SIMULST_OK) return rc;
+
+    MmaParams prm{};
+    prm.p = p_choose; prm.e = soft ? soft_energy : nullptr; prm.mask = padding_mask;
+    prm.alpha = alpha; prm.beta = soft ? beta : nullptr; prm.side = side;
+    prm.N = N; prm.T = T; prm.S = S; prm.eps = eps; prm.chunk = chunk_size; prm.flags = flags;
+    prm.status = status;
+    prm.tma = g_use_tma && ((size_t)S * esz) % 16 == 0 && aligned(p_choose, 16) &&
+              (!soft || aligned(soft_energy, 16));
+    prm.vec_out = (S % 4 == 0) && aligned(alpha, 16) && (!soft || aligned(beta, 16));
+
+    const Config cfg = pick_config(S);
+    const int mode = mode_of(flags, chunk_size);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (p_dtype) {
+        case SIMULST_F32: return mma_fwd_dispatch_f32(prm, mode, cfg.threads, cfg.vpt, st);
+        case SIMULST_BF16: return mma_fwd_dispatch_bf16(prm, mode, cfg.threads, cfg.vpt, st);
+        default: return mma_fwd_dispatch_f16(prm, mode, cfg.threads, cfg.vpt, st);
+    }
+}
+
+int simulst_mma_train_bwd(const void* p_choose, int p_dtype, const void* soft_energy, int e_dtype,
+                          const uint8_t* padding_mask, const float* alpha, const float* side,
+                          const float* grad_alpha, const float* grad_beta,
+                          void* grad_p, int gp_dtype, void* grad_energy, int ge_dtype,
+                          int N, int T, int S, float eps, int chunk_size, unsigned flags,
+                          void* stream) {
+    const bool soft = (flags & SIMULST_MMA_SOFT) != 0u;
+    const bool mp = (flags & SIMULST_MMA_MASS_PRESERVATION) != 0u;
+    if (p_choose == nullptr || alpha == nullptr || grad_p == nullptr || !valid_dtype(p_dtype)) return SIMULST_E_ARG;
+    if (gp_dtype != p_dtype) return SIMULST_E_ARG;
+    if (soft && (soft_energy == nullptr || grad_energy == nullptr || e_dtype != p_dtype || ge_dtype != p_dtype))
+        return SIMULST_E_ARG;
+    if (!soft && grad_beta != nullptr) return SIMULST_E_ARG;
+    if (mp && side == nullptr) return SIMULST_E_ARG;
+    if (chunk_size < 0) return SIMULST_E_ARG;
+    if (N < 0 || T < 0 || S < 0 || S > SIMULST_MMA_MAX_SRC) return SIMULST_E_SHAPE;
+    if (N == 0 || T == 0 || S == 0) return SIMULST_OK;
+    const size_t esz = dtype_size(p_dtype);
+    if (!aligned(p_choose, esz) || !aligned(grad_p, esz) || !aligned(alpha, 4)) return SIMULST_E_ALIGN;
+    int rc = check_device();
+    if (rc != SIMULST_OK) return rc;
+
+    MmaParams prm{};
+    prm.p = p_choose; prm.e = soft ? soft_energy : nullptr; prm.mask = padding_mask;
+    prm.alpha = const_cast<float*>(alpha); prm.side = const_cast<float*>(side);
+    prm.g_alpha = grad_alpha; prm.g_beta = soft ? grad_beta : nullptr;
+    prm.g_p = grad_p; prm.g_e = soft ? grad_energy : nullptr;
+    prm.N = N; prm.T = T; prm.S = S; prm.eps = eps; prm.chunk = chunk_size; prm.flags = flags;
+    prm.status = nullptr;
+    const bool a16 = aligned(p_choose, 16) && (!soft || aligned(soft_energy, 16)) && aligned(alpha, 16) &&
+                     (grad_alpha == nullptr || aligned(grad_alpha, 16)) &&
+                     (grad_beta == nullptr || aligned(grad_beta, 16)) && aligned(grad_p, 16) &&
+                     (!soft || aligned(grad_energy, 16));
+    prm.tma = g_use_tma && ((size_t)S * esz) % 16 == 0 && a16;
+    prm.vec_out = ((size_t)S * esz) % 16 == 0 && (S % 4 == 0) && a16;
+
+    const Config cfg = pick_config(S);
+    const int mode = mode_of(flags, chunk_size);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (p_dtype) {
+        case SIMULST_F32: return mma_bwd_dispatch_f32(prm, mode, cfg.threads, cfg.vpt, st);
+        case SIMULST_BF16: return mma_bwd_dispatch_bf16(prm, mode, cfg.threads, cfg.vpt, st);
+        default: return mma_bwd_dispatch_f16(prm, mode, cfg.threads, cfg.vpt, st);
+    }
+}
+
+}  // extern "C"

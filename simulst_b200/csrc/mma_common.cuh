@@ -1,0 +1,127 @@
+// Pieces shared by the MMA training forward and backward kernels.
+#pragma once
+
+#include "common.cuh"
+
+namespace simulst {
+
+constexpr int kModeHard = 0;    // alpha only
+constexpr int kModeSoftIL = 1;  // + infinite-lookback soft attention
+constexpr int kModeSoftCk = 2;  // + chunkwise soft attention (moving_sum windows)
+
+constexpr int kFwdStages = 3;  // depth of the forward row-staging ring
+constexpr int kXSlots = 4;      // values exchanged per block-wide barrier (max)
+constexpr int kXStride = 32;    // one float per warp per slot (<= 32 warps)
+
+struct MmaParams {
+    const void* p;          // [N,T,S]
+    const void* e;          // [N,T,S] or null
+    const uint8_t* mask;    // [N,S] or null
+    float* alpha;           // fwd: out; bwd: saved forward output
+    float* beta;            // fwd: out
+    float* side;            // [N,T,2]
+    const float* g_alpha;   // bwd
+    const float* g_beta;    // bwd
+    void* g_p;              // bwd out
+    void* g_e;              // bwd out
+    int N, T, S;
+    float eps;
+    int chunk;
+    unsigned flags;
+    unsigned* status;
+    int tma;                // 1: rows staged by TMA bulk copies
+    int vec_out;            // 1: fp32 rows may be accessed as float4
+};
+
+// Double-buffered per-warp exchange area in shared memory.
+struct Xchg {
+    float* base;
+    int turn;
+    __device__ __forceinline__ Xchg(float* b) : base(b), turn(0) {}
+    __device__ __forceinline__ float* slot(int s) const {
+        return base + ((turn & 1) * kXSlots + s) * kXStride;
+    }
+    __device__ __forceinline__ void flip() { ++turn; }
+};
+
+// Read VPT consecutive elements of a staged row from shared memory in <=16-byte packs.
+template <typename T, int VPT>
+__device__ __forceinline__ void lds_row(const T* __restrict__ row, int j0, float (&out)[VPT]) {
+    constexpr int PK = (16 / sizeof(T)) < VPT ? (16 / sizeof(T)) : VPT;
+#pragma unroll
+    for (int q = 0; q < VPT / PK; ++q) {
+        Pack<T, PK> pk = *reinterpret_cast<const Pack<T, PK>*>(row + j0 + q * PK);
+#pragma unroll
+        for (int k = 0; k < PK; ++k) out[q * PK + k] = to_f32<T>(pk.v[k]);
+    }
+}
+
+// Global fp32 row access in float4 chunks when legal, scalar otherwise.
+template <int VPT, bool FULL = false>
+__device__ __forceinline__ void st_row_f32(float* __restrict__ row, int j0, int S, bool vec,
+                                           const float (&v)[VPT]) {
+#pragma unroll
+    for (int q = 0; q < VPT / 4; ++q) {
+        const int j = j0 + 4 * q;
+        if constexpr (FULL) {
+            *reinterpret_cast<float4*>(row + j) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else if (vec) {
+            if (j < S) *reinterpret_cast<float4*>(row + j) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (j + k < S) row[j + k] = v[4 * q + k];
+        }
+    }
+}
+template <int VPT>
+__device__ __forceinline__ void ld_row_f32(const float* __restrict__ row, int j0, int S, bool vec,
+                                           float (&v)[VPT]) {
+#pragma unroll
+    for (int q = 0; q < VPT / 4; ++q) {
+        const int j = j0 + 4 * q;
+        if (vec) {
+            float4 t = (j < S) ? *reinterpret_cast<const float4*>(row + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[4 * q + k] = (j + k < S) ? row[j + k] : 0.f;
+        }
+    }
+}
+// Typed global row store (gradients in the activation dtype).
+template <typename T, int VPT, bool FULL = false>
+__device__ __forceinline__ void st_row_t(T* __restrict__ row, int j0, int S, bool vec,
+                                         const float (&v)[VPT]) {
+    constexpr int PK = (16 / sizeof(T)) < VPT ? (16 / sizeof(T)) : VPT;
+#pragma unroll
+    for (int q = 0; q < VPT / PK; ++q) {
+        const int j = j0 + q * PK;
+        if (vec) {
+            if (FULL || j < S) {
+                Pack<T, PK> pk;
+#pragma unroll
+                for (int k = 0; k < PK; ++k) pk.v[k] = from_f32<T>(v[q * PK + k]);
+                *reinterpret_cast<Pack<T, PK>*>(row + j) = pk;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < PK; ++k)
+                if (j + k < S) row[j + k] = from_f32<T>(v[q * PK + k]);
+        }
+    }
+}
+
+// Shared-memory plan of the row-staging ring, identical on host and device.
+struct StagePlan {
+    int n_stage;       // ring depth
+    int row_bytes;     // bytes reserved per staged row (multiple of 128)
+    int rows;          // rows per stage
+    int win_floats;    // chunkwise window scratch (floats), 0 otherwise
+    __host__ __device__ int header_bytes() const { return 128 + 2 * kXSlots * kXStride * 4 + 128; }
+    __host__ __device__ size_t total() const {
+        return (size_t)header_bytes() + (size_t)n_stage * rows * row_bytes + (size_t)win_floats * 4;
+    }
+};
+
+}  // namespace simulst

@@ -1,0 +1,20 @@
+// Kernel-configuration table of the MMA training kernels and the per-dtype dispatchers.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace simulst {
+
+struct MmaParams;
+
+// (threads per CTA, elements per thread); capacity = product >= S
+#define SIMULST_MMA_CONFIGS(X) \
+    X(32, 4) X(32, 8) X(64, 8) X(128, 8) X(256, 8) X(512, 8) X(512, 12) X(512, 16) X(1024, 16)
+
+int mma_fwd_dispatch_f32(const MmaParams&, int mode, int threads, int vpt, cudaStream_t);
+int mma_fwd_dispatch_bf16(const MmaParams&, int mode, int threads, int vpt, cudaStream_t);
+int mma_fwd_dispatch_f16(const MmaParams&, int mode, int threads, int vpt, cudaStream_t);
+int mma_bwd_dispatch_f32(const MmaParams&, int mode, int threads, int vpt, cudaStream_t);
+int mma_bwd_dispatch_bf16(const MmaParams&, int mode, int threads, int vpt, cudaStream_t);
+int mma_bwd_dispatch_f16(const MmaParams&, int mode, int threads, int vpt, cudaStream_t);
+
+}  // namespace simulst

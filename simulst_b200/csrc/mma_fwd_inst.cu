@@ -1,0 +1,33 @@
+// Instantiations of the MMA forward kernel for ONE activation dtype (selected with
+// -DSIMULST_INST_DTYPE=0|1|2 so the three dtypes compile in parallel).
+#include "mma_fwd.cuh"
+#include "mma_dispatch.h"
+
+namespace simulst {
+
+#if SIMULST_INST_DTYPE == 0
+using InstT = float;
+#define INST_NAME mma_fwd_dispatch_f32
+#elif SIMULST_INST_DTYPE == 1
+using InstT = __nv_bfloat16;
+#define INST_NAME mma_fwd_dispatch_bf16
+#else
+using InstT = __half;
+#define INST_NAME mma_fwd_dispatch_f16
+#endif
+
+int INST_NAME(const MmaParams& prm, int mode, int threads, int vpt, cudaStream_t stream) {
+#define X(TH, VP)                                                                         \
+    if (threads == TH && vpt == VP) {                                                     \
+        switch (mode) {                                                                   \
+            case kModeHard: return launch_mma_fwd<TH, VP, InstT, kModeHard>(prm, stream); \
+            case kModeSoftIL: return launch_mma_fwd<TH, VP, InstT, kModeSoftIL>(prm, stream); \
+            case kModeSoftCk: return launch_mma_fwd<TH, VP, InstT, kModeSoftCk>(prm, stream); \
+        }                                                                                 \
+    }
+    SIMULST_MMA_CONFIGS(X)
+#undef X
+    return SIMULST_E_ARG;
+}
+
+}  // namespace simulst
