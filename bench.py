@@ -1,0 +1,450 @@
+#!/usr/bin/env python
+"""Benchmark of the streaming-alignment hot path (BASELINE.json metric, config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One step = one pass of the hot path over one batch: the MMA training shape B=64 utterances x
+H=8 heads, tgt 128, src 1024, bf16 p_choose / soft energy in, fp32 alpha / beta out, fused
+forward + fused backward (2 kernel launches).  Multi-GPU shards the utterance batch: every rank
+processes its own 64 utterances (weak scaling, no data-path collective) and all-reduces a
+stand-in parameter-gradient buffer (1.6 M fp32, the MMA decoder's q/k projections) over NCCL.
+
+Prints ONE JSON line (rank 0).  `value` is whole-job elements/s with inputs resident in HBM;
+`e2e` is the same metric through the C-ABI with HOST (pinned) buffers, copies inside the timed
+region; `roofline` is the dominant kernel (backward) against the measured HBM peak;
+`cpu_baseline` is the oracle port (the reference's algorithm, torch CPU ops) on this box's cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "mma_expected_alignment_fwd_bwd_elements_per_s"
+UNIT = "elements/s"          # element = one (batch, head, tgt, src) cell
+B, H, T, S = 64, 8, 128, 1024
+N_ROWS = B * H
+EPS = 1e-6
+BYTES_FWD, BYTES_BWD = 12, 20    # algorithmic bytes per element, bf16 in (SURVEY 8d / DESIGN.md)
+GRAD_BUF_ELEMS = 6 * 4 * 256 * 256   # stand-in: 6 layers x (q,k,q_soft,k_soft) x 256x256
+CPU_SAMPLE_ROWS = 64                 # bounded CPU sample: 64 of the 512 rows, full T x S
+
+
+def config(n_gpus):
+    return {
+        "workload": "MMA infinite-lookback training shape, fused expected alignment + mass "
+                    "preservation + expected soft attention, forward+backward",
+        "B_per_gpu": B, "H": H, "tgt": T, "src": S, "global_batch": B * n_gpus,
+        "inputs": "bf16 p_choose + soft_energy", "outputs": "fp32 alpha + beta; bf16 grads",
+        "parallelism": f"dp{n_gpus} (utterance batch sharded, NCCL all-reduce of a "
+                       f"{GRAD_BUF_ELEMS * 4 / 1e6:.1f} MB grad buffer)" if n_gpus > 1 else "single GPU",
+        "l2": "inputs+outputs 2.1 GB per step >> 126 MB L2 (no flush needed)",
+    }
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    """dram bytes per launch from the committed ncu summary of the same shape, else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            return json.load(f)[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) > 8 for k in range(4)
+                          if r[5 + k].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- CPU arm
+def cpu_port_step(p, e, ga, gb):
+    """The reference's algorithm (oracle port, torch CPU ops, autograd backward) on a sample."""
+    import torch
+    from oracle import mma as omma
+    p = p.detach().requires_grad_()
+    e = e.detach().requires_grad_()
+    alpha, beta = omma.mma_process_train(p, e, None, EPS, True, None)
+    ((alpha * ga).sum() + (beta * gb).sum()).backward()
+    return p.grad, e.grad
+
+
+def cpu_inputs(rows):
+    import torch
+    g = torch.Generator().manual_seed(1234)
+    p = torch.sigmoid(torch.randn(rows, T, S, generator=g) - 2.0)
+    e = torch.randn(rows, T, S, generator=g)
+    ga = (torch.arange(1, S + 1).float() / S).expand(rows, T, S) + 1e-2 * torch.randn(rows, T, S, generator=g)
+    gb = torch.randn(rows, T, S, generator=g)
+    return p, e, ga, gb
+
+
+def time_cpu(reps, warmup):
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    args = cpu_inputs(CPU_SAMPLE_ROWS)
+    for _ in range(warmup):
+        cpu_port_step(*args)
+    best = float("inf")
+    total = 0.0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_port_step(*args)
+        dt = time.perf_counter() - t0
+        best = min(best, dt)
+        total += dt
+    elems = CPU_SAMPLE_ROWS * T * S
+    return elems / best, elems / (total / reps), total / reps, torch.get_num_threads()
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle port: same
+    torch ops as codebase/utils/monotonic_attention.py; the Python reference itself cannot travel
+    to the GPU box) on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    best, mean, sec, cores = time_cpu(max(1, args.steps), max(1, min(args.warmup, 1)))
+    sample = f"{CPU_SAMPLE_ROWS} of {N_ROWS} rows (full tgt {T} x src {S}), fp32, fwd+bwd, mean of {max(1, args.steps)}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mean, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config(args.gpus),
+        "cpu_baseline": {"value": mean, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": mean, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import simulst_b200
+    from simulst_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    dt = torch.bfloat16
+    # pinned host copies (the e2e leg uploads them every step)
+    p_host = torch.sigmoid(torch.randn(N_ROWS, T, S, generator=g) - 2.0).to(dt).pin_memory()
+    e_host = torch.randn(N_ROWS, T, S, generator=g).to(dt).pin_memory()
+    p = p_host.to(dev, non_blocking=True)
+    e = e_host.to(dev, non_blocking=True)
+    alpha = torch.empty(N_ROWS, T, S, device=dev)
+    beta = torch.empty_like(alpha)
+    side = torch.empty(N_ROWS, T, 2, device=dev)
+    ga = ((torch.arange(1, S + 1, device=dev).float() / S).expand(N_ROWS, T, S)
+          + 1e-2 * torch.randn(N_ROWS, T, S, device=dev)).contiguous()
+    gb = torch.randn(N_ROWS, T, S, device=dev)
+    gp = torch.empty_like(p)
+    ge = torch.empty_like(e)
+    gp_host = torch.empty(N_ROWS, T, S, dtype=dt).pin_memory()
+    ge_host = torch.empty(N_ROWS, T, S, dtype=dt).pin_memory()
+    status = _lib.status_word(dev)
+    grad_buf = torch.randn(GRAD_BUF_ELEMS, device=dev)
+    stream = torch.cuda.current_stream()
+    st = stream.cuda_stream
+    flags = _lib.MMA_MASS_PRESERVATION | _lib.MMA_SOFT
+
+    def fwd():
+        rc = lib.simulst_mma_train_fwd(p.data_ptr(), _lib.BF16, e.data_ptr(), _lib.BF16, None,
+                                       alpha.data_ptr(), beta.data_ptr(), side.data_ptr(),
+                                       N_ROWS, T, S, EPS, 0, flags, status.data_ptr(), st)
+        _lib.check(rc, "simulst_mma_train_fwd")
+
+    def bwd():
+        rc = lib.simulst_mma_train_bwd(p.data_ptr(), _lib.BF16, e.data_ptr(), _lib.BF16, None,
+                                       alpha.data_ptr(), side.data_ptr(), ga.data_ptr(), gb.data_ptr(),
+                                       gp.data_ptr(), _lib.BF16, ge.data_ptr(), _lib.BF16,
+                                       N_ROWS, T, S, EPS, 0, flags, st)
+        _lib.check(rc, "simulst_mma_train_bwd")
+
+    pending = [None]
+
+    def step(timers=None):
+        if timers is not None:
+            timers[0].record(stream)
+        fwd()
+        if timers is not None:
+            timers[1].record(stream)
+        bwd()
+        if timers is not None:
+            timers[2].record(stream)
+        if world > 1:
+            if pending[0] is not None:
+                pending[0].wait()
+            pending[0] = dist.all_reduce(grad_buf, async_op=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing: W warm-up, exactly K timed steps
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    simulst_b200.reset_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_begin.record(stream)
+    for k in range(args.steps):
+        step(ev[k])
+    if pending[0] is not None:
+        pending[0].wait()
+        pending[0] = None
+    t_end.record(stream)
+    barrier()
+    launches = simulst_b200.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = t_begin.elapsed_time(t_end)
+    t_max = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    ms_step = float(t_max.item()) / args.steps
+    fwd_ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)) / args.steps
+    bwd_ms = sum(ev[k][1].elapsed_time(ev[k][2]) for k in range(args.steps)) / args.steps
+    simulst_b200.check_status(dev)
+    elems = N_ROWS * T * S
+    value = elems * world / (ms_step * 1e-3)
+
+    # ---------------- end to end through the C ABI with HOST buffers (copies inside the region)
+    def e2e_step():
+        p.copy_(p_host, non_blocking=True)
+        e.copy_(e_host, non_blocking=True)
+        fwd()
+        bwd()
+        gp_host.copy_(gp, non_blocking=True)
+        ge_host.copy_(ge, non_blocking=True)
+        if world > 1:
+            if pending[0] is not None:
+                pending[0].wait()
+            pending[0] = dist.all_reduce(grad_buf, async_op=True)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t_begin.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    if pending[0] is not None:
+        pending[0].wait()
+        pending[0] = None
+    t_end.record(stream)
+    barrier()
+    e_max = torch.tensor([t_begin.elapsed_time(t_end)], device=dev)
+    if world > 1:
+        dist.all_reduce(e_max, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e_max.item()) / e2e_steps
+    h2d = p_host.numel() * 2 + e_host.numel() * 2
+    d2h = gp_host.numel() * 2 + ge_host.numel() * 2
+
+    extras = {}
+    cpu_base = None
+    if rank == 0 and world == 1:
+        extras = side_benchmarks(lib, dev)
+        best, mean, sec, cores = time_cpu(reps=2, warmup=1)
+        cpu_base = {"value": mean, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{CPU_SAMPLE_ROWS} of {N_ROWS} rows (full tgt {T} x src {S}), fp32, "
+                              f"fwd+bwd, mean of 2 after 1 warm-up ({sec:.2f} s each)"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        ach = elems * BYTES_BWD / (bwd_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config(world),
+            "roofline": {"bound": "hbm", "kernel": "mma_bwd_kernel", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic("mma_bwd_kernel"),
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": elems * BYTES_BWD,
+                         "kernel_ms": bwd_ms,
+                         "fwd": {"kernel": "mma_fwd_kernel", "kernel_ms": fwd_ms,
+                                 "achieved": elems * BYTES_FWD / (fwd_ms * 1e-3) / 1e9,
+                                 "frac": elems * BYTES_FWD / (fwd_ms * 1e-3) / 1e9 / peak,
+                                 "traffic": ncu_traffic("mma_fwd_kernel")},
+                         "fwd_bwd_frac": elems * (BYTES_FWD + BYTES_BWD) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak},
+            "e2e": {"value": elems * world / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        line.update(extras)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def side_benchmarks(lib, dev):
+    """CIF (BASELINE config 3) and the incremental step (config 4): reported next to the headline,
+    N=1 only, not part of `value`."""
+    import torch
+    from simulst_b200 import ops
+    from simulst_b200.models.torch_cif import cif_function
+    out = {}
+    try:
+        g = torch.Generator().manual_seed(2024)
+        b, s, c = 64, 1500, 256
+        x = torch.randn(b, s, c, generator=g).to(dev).requires_grad_()
+        a = torch.sigmoid(torch.randn(b, s, generator=g) - 1.0).to(dev).requires_grad_()
+        tl = a.detach().sum(1).round().clamp(min=1).long()
+        res = cif_function(x, a, beta=1.0, tail_thres=0.5, target_lengths=tl)
+        go = torch.randn_like(res["cif_out"][0])
+        gd = torch.randn_like(res["delays"][0])
+
+        def cif_step():
+            x.grad = None
+            a.grad = None
+            r = cif_function(x, a, beta=1.0, tail_thres=0.5, target_lengths=tl)
+            torch.autograd.backward([r["cif_out"][0], r["delays"][0]], [go, gd])
+
+        for _ in range(3):
+            cif_step()
+        torch.cuda.synchronize()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        reps = 20
+        t0.record()
+        for _ in range(reps):
+            cif_step()
+        t1.record()
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1) / reps
+        t_out = int(res["cif_out"][0].shape[1])
+        alg = b * s * (c * 4 * (3 + 2 * t_out / s) + 8)
+        peak, _ = measured_peak()
+        out["cif"] = {"metric": "cif_fwd_bwd_frames_per_s", "value": b * s / (ms * 1e-3), "unit": "frames/s",
+                      "config": f"B={b} S={s} C={c} fp32 beta=1.0 training mode, T={t_out}",
+                      "ms_per_step": ms, "algorithmic_bytes": alg,
+                      "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak,
+                      "note": "through the Python API incl. 1 host read (T) per forward, as the reference"}
+    except Exception as exc:  # pragma: no cover
+        out["cif"] = {"error": repr(exc)}
+    try:
+        g = torch.Generator().manual_seed(3000)
+        r, s = 256 * 4, 1024
+        p = torch.sigmoid(torch.randn(r, s, generator=g) - 2.0).to(dev)
+        se = torch.randn(r, s, generator=g).to(dev)
+        hs = torch.zeros(r, dtype=torch.long, device=dev)
+        for _ in range(3):
+            ops.mma_step(p, hs, se, None, True)
+        torch.cuda.synchronize()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        reps = 50
+        hs.zero_()
+        t0.record()
+        for _ in range(reps):
+            ops.mma_step(p, hs, se, None, True)
+        t1.record()
+        torch.cuda.synchronize()
+        us = t0.elapsed_time(t1) / reps * 1e3
+        out["incremental_step"] = {"metric": "mma_infer_step_us_per_layer", "value": us, "unit": "us",
+                                   "config": f"256 utterances x 4 heads, src {s}, infinite lookback, fp32",
+                                   "rows_per_s": r / (us * 1e-6)}
+    except Exception as exc:  # pragma: no cover
+        out["incremental_step"] = {"error": repr(exc)}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    args.warmup = max(args.warmup, 3)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: relaunch under torchrun when started as a plain process
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"),
+               os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
+               "--warmup", str(args.warmup)]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

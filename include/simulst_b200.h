@@ -152,9 +152,10 @@ int simulst_moving_sum(const void* x, void* out, int dtype, long long rows, int 
                        int start_idx, int end_idx, void* stream);
 
 /* exclusive_cumprod(x, dim=last, eps) = exp(cumsum(log(cat[1, x] + eps)))[:-1]
- * (functions.py:20-66). */
+ * (functions.py:20-45); inclusive != 0 gives safe_cumprod = exp(cumsum(log(x + eps)))
+ * (functions.py:48-66). */
 int simulst_exclusive_cumprod(const void* x, void* out, int dtype, long long rows, int S,
-                              float eps, unsigned* status, void* stream);
+                              float eps, int inclusive, unsigned* status, void* stream);
 
 /* learnable_p_choose (codebase/utils/p_choose_strategy.py:56-76):
  * out = sigmoid(energy + noise), noise may be NULL (eval).  Same dtype in and out; the
@@ -172,63 +173,71 @@ int simulst_p_choose(const void* energy, const void* noise, void* out, int dtype
  *   src_lengths  [R] int32          valid source length per row; NULL = S for all rows
  *   head_step    [R] int64 in/out   the `head_step` cache (zeros before the first step)
  *   head_read    [R] uint8 out      the `head_read` cache (bool)
- *   alpha        [R,S] o_dtype out  one-hot alignment
- *   beta         [R,S] o_dtype out  softmax over the look-back window; NULL for hard
+ *   alpha        [R,S] p_dtype out  one-hot alignment (zeros_like(p_choose), :261)
+ *   beta         [R,S] e_dtype out  softmax over the look-back window; NULL for hard
+ *   flags        SIMULST_MMA_MASS_PRESERVATION or 0
  */
 int simulst_mma_step(const void* p_choose, int p_dtype,
                      const void* soft_energy, int e_dtype,
                      const int32_t* src_lengths,
                      int64_t* head_step, uint8_t* head_read,
-                     void* alpha, void* beta, int o_dtype,
+                     void* alpha, void* beta,
                      int R, int S, unsigned flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * CIF (continuous integrate-and-fire).  Replaces cif_function
- * (codebase/models/torch_cif/cif.py:23-196) in three launches, with one optional host read
- * (the output length T, exactly where the reference reads `feat_lengths.max()`).
+ * (codebase/models/torch_cif/cif.py:23-196) with a plan pass + a gather pass (+ two backward
+ * passes); the host reads the output length exactly where the reference does
+ * (`feat_lengths.max()`, cif.py:72/76 and :181).
  *
- * Pass 1, simulst_cif_plan: per batch row, scale alpha (training mode), inclusive-scan it,
- * and derive the firing indices.
- *   alpha        [B,S] a_dtype      integration weights (after sigmoid)
- *   padding_mask [B,S] uint8        or NULL
- *   desired_sum  [B] fp32           training mode: beta*target_length+eps as computed by the
- *                                   host wrapper in the input dtype (cif.py:68); NULL = inference
- *   target_lengths [B] int64        training mode lengths; NULL = inference
- *   csum         [B,S] fp32 out     cumsum of the (scaled) weights
- *   alpha_sum    [B] fp32 out       sum of the unscaled masked weights (cif.py:69,74)
- *   lengths      [B] int64 out      feat_lengths before tail handling
- *   t_max        [1] int32 out      max over rows of `lengths` (atomicMax; zero it first)
+ * Pass 1, simulst_cif_plan: per batch row, mask + scale alpha (training mode), inclusive scan.
+ *   alpha          [B,S] a_dtype   integration weights (after sigmoid)
+ *   padding_mask   [B,S] uint8     or NULL
+ *   desired_sum    [B] fp32        training: beta*target_length+eps evaluated by the host
+ *                                  wrapper in the input dtype (cif.py:68); NULL = inference
+ *   target_lengths [B] int64       training lengths; NULL = inference
+ *   csum           [B,S] fp32 out  cumsum of the (scaled, masked) weights (cif.py:79)
+ *   scale          [B] fp32 out    desired_sum / alpha_sum (1 in inference)
+ *   alpha_sum      [B] fp32 out    sum of the masked, unscaled weights (cif.py:69,74)
+ *   lengths        [B] int64 out   feat_lengths before tail handling
+ *   t_max          [1] int32 i/o   inference: atomicMax of lengths (caller zeroes it); may be
+ *                                  NULL in training
  */
 int simulst_cif_plan(const void* alpha, int a_dtype, const uint8_t* padding_mask,
                      const float* desired_sum, const int64_t* target_lengths,
                      float* csum, float* scale, float* alpha_sum, int64_t* lengths,
                      int* t_max, int B, int S, float beta, unsigned* status, void* stream);
 
-/* Pass 2, simulst_cif_fwd: weighted segment sums (gather formulation: every output slot
- * reads one contiguous source range, deterministic, no atomics) plus tail handling.
+/* Pass 2, simulst_cif_fwd: weighted segment sums, one warp per output slot (every slot reads
+ * one contiguous source range; deterministic, no atomics), fused with the inference tail
+ * handling (cif.py:156-188).
  *   input        [B,S,C] x_dtype
- *   T            number of output slots BEFORE tail extension (= *t_max)
- *   T_alloc      rows allocated in cif_out / delays (T in training mode, T+1 in inference)
- *   cif_out      [B,T_alloc,C] x_dtype out
- *   delays       [B,T_alloc] x_dtype out
- *   tail_weights [B] fp32 out (inference only; NULL in training)
- *   lengths      [B] int64 in/out (inference: += 1 where the tail fires)
- *   bounds       [B,T_alloc+2] int32 workspace: first source frame of every output slot
+ *   T            max over rows of `lengths` (firing indices are clipped to it, cif.py:82)
+ *   T_alloc      slots computed per row: T in training, T+1 in inference
+ *   cif_out      [B,T_alloc,C] x_dtype out     delays [B,T_alloc] x_dtype out
+ *   tail_weights [B] fp32 out      (inference)  lengths_out [B] int64 out (inference: lengths
+ *                                  + 1 where the tail fires)   t_max2 [1] int32 i/o: atomicMax of
+ *                                  lengths_out (caller zeroes it)
  */
 int simulst_cif_fwd(const void* input, int x_dtype, const float* csum, const float* scale,
                     const void* alpha, int a_dtype, const uint8_t* padding_mask,
-                    void* cif_out, void* delays, float* tail_weights, int64_t* lengths,
-                    int* bounds, int B, int S, int C, int T, int T_alloc,
+                    void* cif_out, void* delays, float* tail_weights,
+                    const int64_t* lengths, int64_t* lengths_out, int* t_max2,
+                    int B, int S, int C, int T, int T_alloc,
                     float beta, float tail_thres, int training, void* stream);
 
-/* CIF backward: dL/d input and dL/d alpha given dL/d cif_out and dL/d delays. */
+/* CIF backward: dL/d input [B,S,C] and dL/d alpha [B,S] given dL/d cif_out [B,T_out,C],
+ * dL/d delays [B,T_out] (may be NULL) and dL/d alpha_sum [B] (may be NULL).  T_out is the
+ * number of slots the caller kept (T in training; max(lengths_after_tail) in inference).
+ * workspace: 2*B*S floats. */
 int simulst_cif_bwd(const void* input, int x_dtype, const float* csum, const float* scale,
                     const void* alpha, int a_dtype, const uint8_t* padding_mask,
                     const void* grad_out, const void* grad_delays,
                     const float* tail_weights, const int64_t* lengths_before_tail,
+                    const int64_t* lengths_after_tail,
                     const float* alpha_sum, const float* grad_alpha_sum,
                     void* grad_input, void* grad_alpha, float* workspace,
-                    int B, int S, int C, int T, int T_alloc,
+                    int B, int S, int C, int T, int T_out,
                     float beta, float tail_thres, int training, void* stream);
 
 #ifdef __cplusplus

@@ -56,20 +56,20 @@ SIGNATURES = {
     "simulst_moving_sum": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_int,
                                    c_void_p]),
     "simulst_exclusive_cumprod": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_int, c_float,
-                                          c_void_p, c_void_p]),
+                                          c_int, c_void_p, c_void_p]),
     "simulst_p_choose": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p]),
     "simulst_mma_step": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                                 c_void_p, c_void_p, c_int, c_int, c_int, c_uint, c_void_p]),
+                                 c_void_p, c_void_p, c_int, c_int, c_uint, c_void_p]),
     "simulst_cif_plan": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_int, c_int, c_float, c_void_p, c_void_p]),
     "simulst_cif_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
-                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
                                 c_void_p]),
     "simulst_cif_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
-                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
                                 c_void_p]),
 }

@@ -117,3 +117,274 @@ def mma_train(p_choose: Tensor, soft_energy: Optional[Tensor] = None,
     if soft_energy is None:
         beta = alpha
     return alpha, beta
+
+
+# ----------------------------------------------------------------------------- stand-alone MMA pieces
+class SoftAttentionFunction(torch.autograd.Function):
+    """expected_soft_attention as its own operator
+    (reference codebase/utils/monotonic_attention.py:79-152)."""
+
+    @staticmethod
+    def forward(ctx, alpha, soft_energy, padding_mask, chunk_size, eps):
+        lib = _lib.load()
+        dev = _lib.require_cuda(alpha, soft_energy, padding_mask)
+        n, t, s = alpha.shape
+        if tuple(soft_energy.shape) != (n, t, s):
+            raise ValueError("soft_energy must have the shape of alpha")
+        a = alpha.contiguous()
+        e = soft_energy.contiguous()
+        mask = _mask_u8(padding_mask, n, s, dev)
+        flags = _lib.MMA_ENERGY_F16_FILL if e.dtype == torch.float16 else 0
+        beta = torch.empty_like(a)
+        chunk = int(chunk_size) if chunk_size else 0
+        with torch.cuda.device(dev):
+            rc = lib.simulst_soft_attention_fwd(
+                _lib.ptr(a), _lib.dtype_enum(a.dtype), _lib.ptr(e), _lib.dtype_enum(e.dtype),
+                _lib.ptr(mask), _lib.ptr(beta), n, t, s, float(eps), chunk, flags,
+                _lib.ptr(_lib.status_word(dev)), _lib.stream_ptr(dev))
+        _lib.check(rc, "simulst_soft_attention_fwd")
+        _lib.maybe_check(dev)
+        ctx.save_for_backward(a, e, mask)
+        ctx.cfg = (n, t, s, float(eps), chunk, flags)
+        return beta
+
+    @staticmethod
+    def backward(ctx, g_beta):
+        lib = _lib.load()
+        a, e, mask = ctx.saved_tensors
+        n, t, s, eps, chunk, flags = ctx.cfg
+        dev = a.device
+        gb = g_beta.contiguous().to(a.dtype)
+        ga = torch.empty_like(a)
+        ge = torch.empty_like(e)
+        with torch.cuda.device(dev):
+            rc = lib.simulst_soft_attention_bwd(
+                _lib.ptr(a), _lib.dtype_enum(a.dtype), _lib.ptr(e), _lib.dtype_enum(e.dtype),
+                _lib.ptr(mask), _lib.ptr(gb), _lib.ptr(ga), _lib.ptr(ge),
+                n, t, s, eps, chunk, flags, _lib.stream_ptr(dev))
+        _lib.check(rc, "simulst_soft_attention_bwd")
+        return ga, ge, None, None, None
+
+
+class MassPreservationFunction(torch.autograd.Function):
+    """mass_preservation (reference codebase/utils/monotonic_attention.py:155-197).
+    Like the reference it writes IN PLACE when there is no mask or with left padding
+    (``alpha[:, :, -1] = residuals``); with right padding the reference builds new tensors
+    (masked_fill / scatter_add), so the input is cloned first."""
+
+    @staticmethod
+    def forward(ctx, alpha, padding_mask, left_padding):
+        lib = _lib.load()
+        dev = _lib.require_cuda(alpha, padding_mask)
+        n, t, s = alpha.shape
+        mask = _mask_u8(padding_mask, n, s, dev)
+        in_dtype = alpha.dtype
+        in_place = (padding_mask is None) and alpha.dtype == torch.float32 and alpha.is_contiguous()
+        work = alpha if in_place else alpha.float().contiguous().clone()
+        side = torch.empty((n, t, 2), dtype=torch.float32, device=dev)
+        flags = _lib.MMA_LEFT_PADDING if left_padding else 0
+        with torch.cuda.device(dev):
+            rc = lib.simulst_mass_preservation_fwd(
+                _lib.ptr(work), _lib.ptr(mask), _lib.ptr(side), n, t, s, flags,
+                _lib.ptr(_lib.status_word(dev)), _lib.stream_ptr(dev))
+        _lib.check(rc, "simulst_mass_preservation_fwd")
+        _lib.maybe_check(dev)
+        ctx.save_for_backward(mask, side)
+        ctx.cfg = (n, t, s, flags, in_dtype)
+        if in_place:
+            ctx.mark_dirty(alpha)
+            return alpha
+        out = work.to(in_dtype)
+        if padding_mask is None:           # reference mutates its argument in this branch
+            alpha.copy_(out)
+            ctx.mark_dirty(alpha)
+            return alpha
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        mask, side = ctx.saved_tensors
+        n, t, s, flags, in_dtype = ctx.cfg
+        dev = g.device
+        gin = g.contiguous().float()
+        gout = torch.empty_like(gin)
+        with torch.cuda.device(dev):
+            rc = lib.simulst_mass_preservation_bwd(
+                _lib.ptr(gin), _lib.ptr(mask), _lib.ptr(side), _lib.ptr(gout), n, t, s, flags,
+                _lib.stream_ptr(dev))
+        _lib.check(rc, "simulst_mass_preservation_bwd")
+        return gout.to(in_dtype), None, None
+
+
+def moving_sum(x: Tensor, start_idx: int, end_idx: int) -> Tensor:
+    """functions.py:69-125 (forward only: the reference uses it inside expected_soft_attention,
+    whose gradient is SoftAttentionFunction's)."""
+    lib = _lib.load()
+    dev = _lib.require_cuda(x)
+    assert start_idx > 0 and end_idx > 0
+    n, t, s = x.shape
+    xc = x.contiguous()
+    out = torch.empty_like(xc)
+    with torch.cuda.device(dev):
+        rc = lib.simulst_moving_sum(_lib.ptr(xc), _lib.ptr(out), _lib.dtype_enum(xc.dtype), n * t, s,
+                                    int(start_idx), int(end_idx), _lib.stream_ptr(dev))
+    _lib.check(rc, "simulst_moving_sum")
+    return out
+
+
+def exclusive_cumprod_lastdim(x: Tensor, eps: float, inclusive: bool = False) -> Tensor:
+    lib = _lib.load()
+    dev = _lib.require_cuda(x)
+    s = x.shape[-1]
+    xc = x.contiguous()
+    out = torch.empty_like(xc)
+    rows = xc.numel() // max(s, 1)
+    with torch.cuda.device(dev):
+        rc = lib.simulst_exclusive_cumprod(_lib.ptr(xc), _lib.ptr(out), _lib.dtype_enum(xc.dtype), rows, s,
+                                           float(eps), 1 if inclusive else 0,
+                                           _lib.ptr(_lib.status_word(dev)), _lib.stream_ptr(dev))
+    _lib.check(rc, "simulst_exclusive_cumprod")
+    _lib.maybe_check(dev)
+    return out
+
+
+class PChooseFunction(torch.autograd.Function):
+    """sigmoid(energy + noise) (reference codebase/utils/p_choose_strategy.py:56-76)."""
+
+    @staticmethod
+    def forward(ctx, energy, noise):
+        lib = _lib.load()
+        dev = _lib.require_cuda(energy, noise)
+        e = energy.contiguous()
+        nz = noise.contiguous().to(e.dtype) if noise is not None else None
+        out = torch.empty_like(e)
+        with torch.cuda.device(dev):
+            rc = lib.simulst_p_choose(_lib.ptr(e), _lib.ptr(nz), _lib.ptr(out), _lib.dtype_enum(e.dtype),
+                                      e.numel(), _lib.stream_ptr(dev))
+        _lib.check(rc, "simulst_p_choose")
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (p,) = ctx.saved_tensors
+        # d sigmoid = p (1 - p): elementwise on the producer side of the path (torch op)
+        return g * p * (1 - p), None
+
+
+# ----------------------------------------------------------------------------- incremental step
+def mma_step(p_choose: Tensor, head_step: Tensor, soft_energy: Optional[Tensor] = None,
+             src_lengths: Optional[Tensor] = None, mass_preservation: bool = True):
+    """One decoding step for R = bsz*heads rows (reference
+    modules/monotonic_multihead_attention.py:171-299).  `head_step` [R] int64 is updated in
+    place.  Returns (head_read [R] bool, alpha [R,S], beta [R,S] or None)."""
+    lib = _lib.load()
+    dev = _lib.require_cuda(p_choose, head_step, soft_energy, src_lengths)
+    r, s = p_choose.shape
+    p = p_choose.contiguous()
+    e = soft_energy.contiguous() if soft_energy is not None else None
+    if head_step.dtype != torch.int64 or not head_step.is_contiguous() or head_step.numel() != r:
+        raise ValueError("head_step must be a contiguous int64 tensor with bsz*heads elements")
+    lens = src_lengths.to(torch.int32).contiguous() if src_lengths is not None else None
+    head_read = torch.empty(r, dtype=torch.uint8, device=dev)
+    alpha = torch.empty_like(p)
+    beta = torch.empty_like(e) if e is not None else None
+    flags = _lib.MMA_MASS_PRESERVATION if mass_preservation else 0
+    with torch.cuda.device(dev):
+        rc = lib.simulst_mma_step(_lib.ptr(p), _lib.dtype_enum(p.dtype), _lib.ptr(e),
+                                  _lib.dtype_enum(e.dtype) if e is not None else 0, _lib.ptr(lens),
+                                  _lib.ptr(head_step), _lib.ptr(head_read), _lib.ptr(alpha),
+                                  _lib.ptr(beta), r, s, flags, _lib.stream_ptr(dev))
+    _lib.check(rc, "simulst_mma_step")
+    return head_read.view(torch.bool), alpha, beta
+
+
+# ----------------------------------------------------------------------------- CIF
+class CIFFunction(torch.autograd.Function):
+    """cif_function (reference codebase/models/torch_cif/cif.py:23-196): plan + gather forward,
+    frame-gather + row-scan backward."""
+
+    @staticmethod
+    def forward(ctx, input, alpha, padding_mask, target_lengths, beta, tail_thres, eps):
+        lib = _lib.load()
+        dev = _lib.require_cuda(input, alpha, padding_mask, target_lengths)
+        b, s, c = input.shape
+        x = input.contiguous()
+        a = alpha.contiguous()
+        mask = _mask_u8(padding_mask, b, s, dev)
+        training = target_lengths is not None
+        status = _lib.status_word(dev)
+        csum = torch.empty((b, s), dtype=torch.float32, device=dev)
+        scale = torch.empty(b, dtype=torch.float32, device=dev)
+        alpha_sum = torch.empty(b, dtype=torch.float32, device=dev)
+        lengths0 = torch.empty(b, dtype=torch.int64, device=dev)
+        counters = torch.zeros(2, dtype=torch.int32, device=dev)      # t_max, t_max2
+        desired = tl = None
+        if training:
+            tl = target_lengths.long().contiguous()
+            # cif.py:68 -- evaluated in the INPUT dtype, as the reference does
+            desired = (beta * target_lengths.type_as(x) + eps).float().contiguous()
+            t_cap = int(tl.max()) if b > 0 else 0                      # host read, cif.py:72
+        st = _lib.stream_ptr(dev)
+        with torch.cuda.device(dev):
+            rc = lib.simulst_cif_plan(_lib.ptr(a), _lib.dtype_enum(a.dtype), _lib.ptr(mask),
+                                      _lib.ptr(desired), _lib.ptr(tl), _lib.ptr(csum), _lib.ptr(scale),
+                                      _lib.ptr(alpha_sum), _lib.ptr(lengths0),
+                                      counters.data_ptr(), b, s, float(beta), _lib.ptr(status), st)
+            _lib.check(rc, "simulst_cif_plan")
+            if not training:
+                t_cap = int(counters[0].item()) if b > 0 else 0        # host read, cif.py:76
+            t_alloc = t_cap if training else t_cap + 1
+            out = torch.empty((b, t_alloc, c), dtype=x.dtype, device=dev)
+            delays = torch.empty((b, t_alloc), dtype=x.dtype, device=dev)
+            tail_w = lengths1 = None
+            if not training:
+                tail_w = torch.empty(b, dtype=torch.float32, device=dev)
+                lengths1 = torch.empty(b, dtype=torch.int64, device=dev)
+            rc = lib.simulst_cif_fwd(_lib.ptr(x), _lib.dtype_enum(x.dtype), _lib.ptr(csum), _lib.ptr(scale),
+                                     _lib.ptr(a), _lib.dtype_enum(a.dtype), _lib.ptr(mask),
+                                     _lib.ptr(out), _lib.ptr(delays), _lib.ptr(tail_w),
+                                     _lib.ptr(lengths0), _lib.ptr(lengths1),
+                                     counters.data_ptr() + 4, b, s, c, t_cap, t_alloc,
+                                     float(beta), float(tail_thres), 1 if training else 0, st)
+            _lib.check(rc, "simulst_cif_fwd")
+        _lib.maybe_check(dev)
+        if training:
+            t_out = t_cap
+            lengths = lengths0
+        else:
+            t_out = int(counters[1].item()) if b > 0 else 0            # host read, cif.py:181
+            lengths = lengths1
+        ctx.save_for_backward(x, a, mask, csum, scale, alpha_sum, tail_w, lengths0, lengths1)
+        ctx.cfg = (b, s, c, t_cap, t_out, float(beta), float(tail_thres), training, alpha.dtype)
+        out_v = out[:, :t_out]
+        delays_v = delays[:, :t_out]
+        asum = alpha_sum.to(alpha.dtype)
+        tail_ret = tail_w if tail_w is not None else alpha_sum.new_empty(0)
+        ctx.mark_non_differentiable(lengths, tail_ret)
+        return out_v, delays_v, asum, lengths, tail_ret
+
+    @staticmethod
+    def backward(ctx, g_out, g_delays, g_asum, _g_len, _g_tail):
+        lib = _lib.load()
+        x, a, mask, csum, scale, alpha_sum, tail_w, lengths0, lengths1 = ctx.saved_tensors
+        b, s, c, t_cap, t_out, beta, tail_thres, training, a_dtype = ctx.cfg
+        dev = x.device
+        go = (g_out.contiguous().to(x.dtype) if g_out is not None
+              else torch.zeros((b, t_out, c), dtype=x.dtype, device=dev))
+        gd = g_delays.contiguous().to(x.dtype) if g_delays is not None else None
+        gs = g_asum.contiguous().float() if g_asum is not None else None
+        gx = torch.empty_like(x)
+        ga = torch.empty_like(a)
+        ws = torch.empty(2 * b * s, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.simulst_cif_bwd(_lib.ptr(x), _lib.dtype_enum(x.dtype), _lib.ptr(csum), _lib.ptr(scale),
+                                     _lib.ptr(a), _lib.dtype_enum(a.dtype), _lib.ptr(mask),
+                                     _lib.ptr(go), _lib.ptr(gd), _lib.ptr(tail_w), _lib.ptr(lengths0),
+                                     _lib.ptr(lengths1), _lib.ptr(alpha_sum), _lib.ptr(gs),
+                                     _lib.ptr(gx), _lib.ptr(ga), _lib.ptr(ws),
+                                     b, s, c, t_cap, t_out, beta, tail_thres, 1 if training else 0,
+                                     _lib.stream_ptr(dev))
+        _lib.check(rc, "simulst_cif_bwd")
+        return gx, ga, None, None, None, None, None

@@ -1,0 +1,52 @@
+"""CPU: the C-ABI library loads and exports every symbol include/simulst_b200.h declares; the
+host wrappers refuse to run without CUDA (no CPU fallback)."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "simulst_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(simulst_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    from simulst_b200 import _lib
+    if not os.path.isfile(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == declared
+    assert lib.simulst_version() == 100
+    assert b"argument" in lib.simulst_error_string(-1)
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    from simulst_b200 import _lib
+    lib = _lib.load()
+    assert lib.simulst_mma_set_config(7, 3) == -1
+    assert lib.simulst_mma_set_config(0, 0) == 0
+    # null pointers / bad dtype are rejected before any CUDA call
+    assert lib.simulst_mma_train_fwd(None, 0, None, 0, None, None, None, None, 1, 1, 1, 1e-6, 0, 0, None, None) == -1
+    assert lib.simulst_cif_plan(None, 0, None, None, None, None, None, None, None, None, 1, 1, 1.0, None, None) == -1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    import simulst_b200
+    from simulst_b200.utils.monotonic_attention import expected_alignment_from_p_choose
+    from simulst_b200.models.torch_cif import cif_function
+    with pytest.raises(simulst_b200.BackendUnavailable):
+        expected_alignment_from_p_choose(torch.rand(1, 2, 8))
+    with pytest.raises(simulst_b200.BackendUnavailable):
+        cif_function(torch.rand(1, 4, 2), torch.rand(1, 4))
