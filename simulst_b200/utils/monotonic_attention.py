@@ -17,9 +17,12 @@ def expected_alignment_from_p_choose(
     """monotonic_attention.py:12-76.  p_choose: bsz, tgt_len, src_len; returns alpha in
     p_choose's dtype (:72)."""
     alpha, _ = ops.mma_train(p_choose, None, padding_mask, eps=eps, mass_preservation=False)
+    # The operator keeps its fp32 output for the recompute-based backward.  Callers of this
+    # stand-alone function may write into the result (mass_preservation does, in place, like the
+    # reference), so they get their own tensor.  The fused path (mma_process_train) has no copy.
     if alpha.dtype != p_choose.dtype:
-        alpha = alpha.type(p_choose.dtype)
-    return alpha
+        return alpha.type(p_choose.dtype)
+    return alpha.clone()
 
 
 def expected_soft_attention(

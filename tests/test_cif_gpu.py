@@ -15,6 +15,31 @@ pytestmark = pytest.mark.gpu
 
 CIF = load("cif.npz")
 DEV = "cuda"
+ULP = 2.0 ** -23
+
+
+def cif_tols(x, beta, t_len, s_len):
+    """CIF weights are differences of the running sum of alpha, whose magnitude reaches T*beta, so
+    ANY fp32 evaluation (the reference's included) carries an absolute error of a few ulp(T*beta)
+    in every weight.  Allow 4 ulp of the largest running sum on the weights, propagated to each
+    output: x |x|max for features / input gradients, x S/beta for delays."""
+    w_err = 4 * ULP * max(t_len * beta, 1.0)
+    return {"feat": w_err * float(x.abs().max()), "delay": w_err * s_len / beta}
+
+
+def fp64_oracle(x, a, beta, mask, tl, g_out=None, g_delay=None):
+    x6 = x.double().requires_grad_()
+    a6 = a.double().requires_grad_()
+    r6 = ocif.cif_function(x6, a6, beta=beta, tail_thres=beta / 2, padding_mask=mask,
+                           target_lengths=tl, compute_dtype=torch.float64)
+    if g_out is not None and tuple(r6["cif_out"][0].shape) == tuple(g_out.shape):
+        ((r6["cif_out"][0] * g_out).sum() + (r6["delays"][0] * g_delay).sum()).backward()
+        return r6, x6.grad, a6.grad
+    return r6, None, None
+
+
+def same_shape(a, b):
+    return a if (a is not None and tuple(a.shape) == tuple(b.shape)) else None
 
 
 def _run(x, a, beta, tail_thres, mask, tl, g_out=None, g_delay=None, dtype=torch.float32):
@@ -41,15 +66,19 @@ def test_cif_matches_reference_golden(name):
                          c.g_out, c.g_delay)
     assert torch.equal(res["cif_lengths"][0].cpu(), c.cif_lengths)
     assert tuple(res["cif_out"][0].shape) == tuple(c.cif_out.shape)
-    assert_parity(res["cif_out"][0].detach().cpu(), c.cif_out, "cif_out")
-    assert_parity(res["delays"][0].detach().cpu(), c.delays, "delays")
+    tol = cif_tols(c.input, beta, c.cif_out.shape[1], s)
+    r6, gx6, ga6 = fp64_oracle(c.input, c.alpha, beta, opt(c.mask), opt(c.target_lengths), c.g_out, c.g_delay)
+    assert_parity(res["cif_out"][0].detach().cpu(), c.cif_out, "cif_out",
+                  same_shape(r6["cif_out"][0].detach(), c.cif_out), tol["feat"])
+    assert_parity(res["delays"][0].detach().cpu(), c.delays, "delays",
+                  same_shape(r6["delays"][0].detach(), c.delays), tol["delay"])
     assert_parity(res["alpha_sum"][0].detach().cpu(), c.alpha_sum, "alpha_sum")
     if not train:
-        assert_parity(res["tail_weights"][0].cpu(), c.tail_weights, "tail_weights")
+        assert_parity(res["tail_weights"][0].cpu(), c.tail_weights, "tail_weights", None, tol["feat"])
     else:
         assert res["tail_weights"] == []
-    assert_parity(gx, c.grad_input, "grad_input")
-    assert_parity(ga, c.grad_alpha, "grad_alpha")
+    assert_parity(gx, c.grad_input, "grad_input", gx6, tol["feat"])
+    assert_parity(ga, c.grad_alpha, "grad_alpha", ga6, 1e-4 * float(c.grad_alpha.abs().max()))
 
 
 def _seeded(b, s, c, seed, mu=-1.0, masked=True):
@@ -87,12 +116,20 @@ def test_cif_matches_oracle(b, s, c, beta, train):
     # one frame earlier/later (north_star); none of the seeded cases has one -- asserted here
     res, (gx, ga) = _run(x, a, beta, beta / 2, mask, tl, g_out, g_delay)
     assert torch.equal(res["cif_lengths"][0].cpu(), ref["cif_lengths"][0])
-    assert_parity(res["cif_out"][0].detach().cpu(), ref["cif_out"][0].detach(), "cif_out")
-    assert_parity(res["delays"][0].detach().cpu(), ref["delays"][0].detach(), "delays")
-    assert_parity(gx, xo.grad, "grad_input")
-    assert_parity(ga, ao.grad, "grad_alpha")
+    tol = cif_tols(x, beta, ref["cif_out"][0].shape[1], s)
+    r6, gx6, ga6 = fp64_oracle(x, a, beta, mask, tl, g_out, g_delay)
+    assert_parity(res["cif_out"][0].detach().cpu(), ref["cif_out"][0].detach(), "cif_out",
+                  same_shape(r6["cif_out"][0].detach(), ref["cif_out"][0]), tol["feat"])
+    assert_parity(res["delays"][0].detach().cpu(), ref["delays"][0].detach(), "delays",
+                  same_shape(r6["delays"][0].detach(), ref["delays"][0]), tol["delay"])
+    assert_parity(gx, xo.grad, "grad_input", gx6, tol["feat"])
+    assert_parity(ga, ao.grad, "grad_alpha", ga6, 1e-4 * float(ao.grad.abs().max()))
     if not train:
-        assert_parity(res["tail_weights"][0].cpu(), ref["tail_weights"][0].detach(), "tail")
+        # inference mode has no rescaling of alpha: with the fp64-accumulated scan the firing
+        # structure AND the values coincide with the reference's to the last bit or ulp
+        assert_parity(res["tail_weights"][0].cpu(), ref["tail_weights"][0].detach(), "tail", None, tol["feat"])
+        torch.testing.assert_close(res["cif_out"][0].detach().cpu(), ref["cif_out"][0].detach(),
+                                   rtol=1e-5, atol=1e-5)
 
 
 def test_cif_against_sequential_checker():
