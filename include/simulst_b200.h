@@ -72,6 +72,9 @@ void simulst_reset_launch_count(void);
 int simulst_mma_set_config(int threads, int vpt);
 /* 1 = stage rows with TMA bulk copies when alignment allows (default), 0 = cooperative loads */
 int simulst_mma_set_tma(int enable);
+/* 1 = software-pipelined training kernels for hard / infinite-lookback attention when rows
+ * can be TMA-staged (default), 0 = always the generic (one scan per barrier) kernels */
+int simulst_mma_set_pipeline(int enable);
 
 /* ---------------------------------------------------------------------------------------
  * MMA training path, forward.   Replaces, fused in one launch,

@@ -35,6 +35,7 @@ SIGNATURES = {
     "simulst_reset_launch_count": (None, []),
     "simulst_mma_set_config": (c_int, [c_int, c_int]),
     "simulst_mma_set_tma": (c_int, [c_int]),
+    "simulst_mma_set_pipeline": (c_int, [c_int]),
     "simulst_mma_train_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p,
                                       c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_float, c_int, c_uint,

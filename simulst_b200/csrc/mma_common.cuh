@@ -31,6 +31,7 @@ struct MmaParams {
     unsigned* status;
     int tma;                // 1: rows staged by TMA bulk copies
     int vec_out;            // 1: fp32 rows may be accessed as float4
+    int pipe;               // 1: software-pipelined kernels (hard / infinite lookback, needs tma)
 };
 
 // Double-buffered per-warp exchange area in shared memory.

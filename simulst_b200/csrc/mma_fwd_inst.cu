@@ -1,6 +1,7 @@
 // Instantiations of the MMA forward kernel for ONE activation dtype (selected with
 // -DSIMULST_INST_DTYPE=0|1|2 so the three dtypes compile in parallel).
 #include "mma_fwd.cuh"
+#include "mma_fwd_pipe.cuh"
 #include "mma_dispatch.h"
 
 namespace simulst {
@@ -19,6 +20,10 @@ using InstT = __half;
 int INST_NAME(const MmaParams& prm, int mode, int threads, int vpt, cudaStream_t stream) {
 #define X(TH, VP)                                                                         \
     if (threads == TH && vpt == VP) {                                                     \
+        if constexpr (TH <= kPipeMaxThreads) {                                            \
+            if (prm.tma && prm.pipe && mode == kModeHard) return launch_mma_fwd_pipe<TH, VP, InstT, false>(prm, stream); \
+            if (prm.tma && prm.pipe && mode == kModeSoftIL) return launch_mma_fwd_pipe<TH, VP, InstT, true>(prm, stream); \
+        }                                                                                 \
         switch (mode) {                                                                   \
             case kModeHard: return launch_mma_fwd<TH, VP, InstT, kModeHard>(prm, stream); \
             case kModeSoftIL: return launch_mma_fwd<TH, VP, InstT, kModeSoftIL>(prm, stream); \

@@ -41,17 +41,18 @@ def timeit(fn, reps=5):
     return min(ts), sorted(ts)[len(ts) // 2]
 
 el = N * T * S
-for cfg in [(128, 8), (256, 8)]:
+import os
+for cfg in [(128, 8)]:
     if cfg[0] * cfg[1] < S:
         continue
-    for tma in (1,):
+    for tma in ([0, 1] if os.environ.get("BOTH") else [1]):
         assert lib.simulst_mma_set_config(*cfg) == 0
-        lib.simulst_mma_set_tma(tma)
+        lib.simulst_mma_set_pipeline(tma)
         fwd(); bwd(); torch.cuda.synchronize()
         f_min, f_med = timeit(fwd)
         b_min, b_med = timeit(bwd)
-        print(f"cfg={cfg} tma={tma}: fwd {f_med:8.1f} us ({el*12/f_med/1e3:7.1f} GB/s)  "
+        print(f"cfg={cfg} pipe={tma}: fwd {f_med:8.1f} us ({el*12/f_med/1e3:7.1f} GB/s)  "
               f"bwd {b_med:8.1f} us ({el*20/b_med/1e3:7.1f} GB/s)  "
               f"fwd+bwd {el/(f_med+b_med)*1e6/1e9:7.2f} Gelem/s  frac={el*32/(f_med+b_med)/1e3/6540.2:.3f}",
               flush=True)
-lib.simulst_mma_set_config(0, 0); lib.simulst_mma_set_tma(1)
+lib.simulst_mma_set_config(0, 0); lib.simulst_mma_set_pipeline(1)
