@@ -21,8 +21,11 @@ int INST_NAME(const MmaParams& prm, int mode, int threads, int vpt, cudaStream_t
 #define X(TH, VP)                                                                         \
     if (threads == TH && vpt == VP) {                                                     \
         if constexpr (TH <= kPipeMaxThreads) {                                            \
-            if (prm.tma && prm.pipe && mode == kModeHard) return launch_mma_fwd_pipe<TH, VP, InstT, false>(prm, stream); \
-            if (prm.tma && prm.pipe && mode == kModeSoftIL) return launch_mma_fwd_pipe<TH, VP, InstT, true>(prm, stream); \
+            if (prm.tma && prm.pipe && mode != kModeSoftCk) {                             \
+                const int rc = mode == kModeHard ? launch_mma_fwd_pipe<TH, VP, InstT, false>(prm, stream) \
+                                                 : launch_mma_fwd_pipe<TH, VP, InstT, true>(prm, stream); \
+                if (rc != 1) return rc;         /* 1 = row too long for the pipelined kernel */ \
+            }                                                                             \
         }                                                                                 \
         switch (mode) {                                                                   \
             case kModeHard: return launch_mma_fwd<TH, VP, InstT, kModeHard>(prm, stream); \

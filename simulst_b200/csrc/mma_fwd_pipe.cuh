@@ -1,23 +1,29 @@
 // MMA training forward, software-pipelined: expected alignment (+ mass preservation)
 // (+ infinite-lookback expected soft attention), one CTA per (batch*head) row.
 //
-// Per target step i the work splits into a step-INVARIANT part (functions of p_i / E_i only:
-// exclusive cumprod, clamped divisor, P, exp, the D prefix) and the RECURRENCE
-// (u-prefix over alpha_{i-1} -> alpha_i -> r-suffix -> beta_i).  Loop iteration i runs the
-// recurrence of step i and the invariant part of step i+1 in the same instruction stream and
-// lets their block-wide scans share barriers: 2 __syncthreads per step instead of 4, and two
-// independent dependency chains for the scheduler to interleave.
+// The only true dependency between target steps is  alpha_{i-1} -> u-prefix -> alpha_i.
+// Everything else is either a function of the inputs of one step (exclusive cumprod, clamped
+// divisor, P, row max, exp, D prefix) or hangs off alpha_i without feeding back (row sum,
+// r-suffix, beta_i).  The kernel therefore keeps FOUR steps in flight and lets all their
+// block-wide scans share ONE __syncthreads per loop iteration `it`:
 //
-//   phase A   rec: u-prefix (local + warp)        inv: load row i+1, cumprod (local + warp), max E
-//   ---- barrier A  (then: TMA refill of the ring slot just read)
-//   phase B   rec: alpha_i, r-suffix, row sum     inv: cp, 1/c, P, exp, e-prefix (local + warp)
-//   ---- barrier B
-//   phase C   rec: beta_i, stores                 inv: 1/D
+//   stage MAXS(it+2)  row max of soft_energy                         (REDUX)
+//   stage INV (it+1)  cumprod prefix-product, exp + D prefix-sum     (2 warp scans)
+//   stage RECU(it)    u-prefix over alpha_{it-1}  -> alpha_it        (1 warp scan)
+//   stage RECR(it-1)  r-suffix, row sum           -> beta_{it-1}, mass-preserved column
 //
-// Rows of p_choose / soft_energy arrive through a ring of TMA 1-D bulk copies (UBLKCP) issued
-// NS steps ahead by one thread.  Math / reference lines: see mma_steps.cuh and mma_fwd.cuh.
-// Chunkwise soft attention and rows that TMA cannot stage (not 16-byte aligned) use the
-// generic kernel in mma_fwd.cuh.
+//   PRE : thread-local chains + warp scans of all four stages, one value per warp and scan
+//         published in shared memory
+//   ---- barrier (then: TMA refill of the ring slot INV just consumed)
+//   POST: cross-warp combines, element-wise finish of every stage, stores
+//
+// so the per-step latency is one scan deep instead of four, and the four independent shuffle
+// chains interleave in one instruction stream.  Rows of p_choose / soft_energy arrive through
+// a ring of TMA 1-D bulk copies (UBLKCP) issued NS steps ahead by one thread; exp(E - m) + eps
+// waits for its beta in a thread-private shared-memory stash (3 steps deep).
+// Math / reference lines: mma_steps.cuh and mma_fwd.cuh.  Chunkwise soft attention, rows that
+// TMA cannot stage (not 16-byte aligned) and rows too long for two ring stages use the generic
+// kernel in mma_fwd.cuh.
 #pragma once
 
 #include "mma_common.cuh"
@@ -27,20 +33,33 @@ namespace simulst {
 
 constexpr int kPipeStages = 4;          // deepest row-staging ring (shallower when rows are long)
 constexpr int kPipeMaxThreads = 512;    // 1024-thread CTAs (64 registers/thread) keep the generic kernel
+constexpr int kPipeSlots = 8;           // values exchanged per barrier (6 used)
+constexpr int kExStash = 3;             // steps between exp(E - m) and its use in beta
+
+struct PipePlan {
+    int n_stage;       // ring depth (>= 2 with soft attention)
+    int row_bytes;     // bytes reserved per staged row (multiple of 128)
+    int rows;          // rows per stage (p [, energy])
+    int stash_bytes;   // exp stash: kExStash * THREADS * VPT * 4, 0 without soft attention
+    __host__ __device__ int header_bytes() const { return 128 + 2 * kPipeSlots * kXStride * 4 + 128; }
+    __host__ __device__ size_t total() const {
+        return (size_t)header_bytes() + (size_t)n_stage * rows * row_bytes + (size_t)stash_bytes;
+    }
+};
 
 template <int THREADS, int VPT, typename T, bool SOFT, bool FULL>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 4 : (THREADS <= 256 ? 2 : 1)))
-mma_fwd_pipe_kernel(const MmaParams prm, const StagePlan plan) {
+mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
     constexpr int NW = THREADS / kWarp;
     constexpr int H = VPT / 2;
     static_assert(VPT % 4 == 0, "VPT must be a multiple of 4");
 
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-    float* xA = reinterpret_cast<float*>(smem + 128);       // exchange buffer of barrier A
-    float* xB = xA + kXSlots * kXStride;                    // exchange buffer of barrier B
-    float* bcast = xA + 2 * kXSlots * kXStride;             // [2] 1/D at the mass-preservation column
+    float* xbuf = reinterpret_cast<float*>(smem + 128);               // [2][kPipeSlots][32]
+    float* bcast = xbuf + 2 * kPipeSlots * kXStride;                  // [4] 1/D at the mass-preservation column
     unsigned char* stage0 = smem + plan.header_bytes();
+    float4* stash = reinterpret_cast<float4*>(stage0 + (size_t)plan.n_stage * plan.rows * plan.row_bytes);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = blockIdx.x;
@@ -84,11 +103,11 @@ mma_fwd_pipe_kernel(const MmaParams prm, const StagePlan plan) {
     }
     if (mp_add) {
         const float cnt = warp_sum((float)n_live);
-        if (lane == 0) xA[warp] = cnt;
+        if (lane == 0) xbuf[warp] = cnt;
     }
     __syncthreads();
     if (mp_add) {
-        last = (int)combine_sum<NW>(xA, lane) - 1;
+        last = (int)combine_sum<NW>(xbuf, lane) - 1;
         __syncthreads();
     }
     // element of this thread that sits on the mass-preservation column (-1: none)
@@ -99,6 +118,7 @@ mma_fwd_pipe_kernel(const MmaParams prm, const StagePlan plan) {
         k_last = last - j0;
     }
     const bool own_last = mp && k_last >= 0;
+    auto at_last = [&](int k) -> bool { return (FULL ? k == VPT - 1 : true) && k == k_last; };
 
     // ---- row staging ring
     const unsigned row_bytes = (unsigned)(S * sizeof(T));
@@ -114,43 +134,85 @@ mma_fwd_pipe_kernel(const MmaParams prm, const StagePlan plan) {
     }
 
     const float one_eps = 1.0f + eps;       // first element of the exclusive cumprod (functions.py:28-33)
-    // recurrence state and the invariants of the step the recurrence is about to run
-    float2 a_prev[H], rc[H], P[H], ex[H], rD[H];
+    // state carried between iterations
+    float2 a_prev[H];                       // alpha_{it-1} (before mass preservation)
+    float2 rc[H], P[H], rD[H];              // invariants of the step RECU runs next
+    float2 Rl[H];                           // thread-local r-suffix of the step RECR finishes next
 #pragma unroll
     for (int q = 0; q < H; ++q) {
         a_prev[q] = make_float2((j0 + 2 * q == 0) ? 1.0f : 0.0f, 0.0f);
-        rc[q] = P[q] = ex[q] = rD[q] = f2(0.f);
+        rc[q] = P[q] = rD[q] = Rl[q] = f2(0.f);
     }
+    float m_cur = 0.f;                      // row max of the step INV runs next
+    float rt_prev = 0.f, rsum_prev = 0.f;   // thread totals (r-suffix, row sum) of the step RECR scans next
+    float a_last_raw = 0.f;                 // owner thread: alpha at the mass-preservation column
     unsigned umax = 0u;                     // FULL rows: first-level prob_check
     bool bad = false;                       // ragged rows: exact per-element check
     bool nan_out = false;
 
-    int slot = 0;                           // ring slot holding the row of the NEXT invariant step
-    unsigned parity = 0u;
+    // ring slot / mbarrier parity of row it+1 (INV); MAXS reads the next slot.  The first
+    // iteration is it = -2, i.e. "row -1": the last slot of the previous lap.
+    int slotI = NS - 1;
+    unsigned parI = 1u;
+    int sb_w = kExStash - 1;                // exp-stash buffer of step it+1 (INV writes it); RECR(it-1) reads the next one
 
-    // One loop iteration: recurrence of step `i` (REC) + invariant part of step `i + 1` (INV).
-    auto body = [&](auto rec_c, auto inv_c, const int i) {
-        constexpr bool REC = decltype(rec_c)::value;
-        constexpr bool INV = decltype(inv_c)::value;
+    auto body = [&](auto steady_c, const int it) {
+        constexpr bool STEADY = decltype(steady_c)::value;
+        const bool doM = SOFT && (STEADY || it + 2 < T_len);
+        const bool doI = STEADY || (it >= -1 && it + 1 < T_len);
+        const bool doU = STEADY || (it >= 0 && it < T_len);
+        const bool doR = STEADY || (it >= 1 && it - 1 < T_len);
+        float* xw = xbuf + (it & 1) * (kPipeSlots * kXStride);
 
-        // ================================================= phase A
-        float2 sl[H];
-        float uinc = 0.f, uexc = 0.f;
-        if constexpr (REC) {
-            const float ut = local_u_prefix<VPT>(a_prev, rc, sl);
-            nan_out = nan_out || (ut != ut);     // NaN anywhere in u poisons the thread total
-            uinc = wscan_prefix_add(ut);
-            if (lane == 31) xA[0 * kXStride + warp] = uinc;
-            uexc = wprev(uinc, 0.f);
+        // ================================================================ PRE
+        // thread-local chains of every stage first, then ONE fused warp-scan section (stages that
+        // are off in an edge iteration contribute identities), then the per-warp values go to
+        // shared memory.
+        // ---- MAXS(it+2)
+        float em = -INFINITY;
+        if (SOFT && doM) {
+            int slotM = slotI + 1;
+            unsigned parM = parI;
+            if (slotM == NS) { slotM = 0; parM ^= 1u; }
+            mbar_wait(&bars[slotM], parM);
+            if constexpr (FULL && sizeof(T) == 2 && VPT % 8 == 0) {
+                // packed 16-bit max, one conversion at the end
+                using T2 = typename std::conditional<std::is_same<T, __half>::value, __half2, __nv_bfloat162>::type;
+                const uint4* src = reinterpret_cast<const uint4*>(stage_e(slotM) + j0);
+                T2 acc;
+#pragma unroll
+                for (int q = 0; q < VPT / 8; ++q) {
+                    const uint4 w = src[q];
+                    const T2 a = __hmax2(*reinterpret_cast<const T2*>(&w.x), *reinterpret_cast<const T2*>(&w.y));
+                    const T2 b = __hmax2(*reinterpret_cast<const T2*>(&w.z), *reinterpret_cast<const T2*>(&w.w));
+                    const T2 c = __hmax2(a, b);
+                    acc = q == 0 ? c : __hmax2(acc, c);
+                }
+                em = fmaxf(to_f32<T>(acc.x), to_f32<T>(acc.y));
+            } else {
+                float2 Em[H];
+                unsigned dummy = 0u;
+                lds_row2<T, VPT, false>(stage_e(slotM) + j0, Em, dummy);
+                if constexpr (!FULL) {
+#pragma unroll
+                    for (int k = 0; k < VPT; ++k)
+                        if (!is_live(k)) SIMULST_EL(Em, k) = is_in(k) ? fill : -INFINITY;
+                }
+                em = fmaxf(Em[0].x, Em[0].y);
+#pragma unroll
+                for (int q = 1; q < H; ++q) em = fmaxf(em, fmaxf(Em[q].x, Em[q].y));
+            }
         }
-        float2 p_n[H], E_n[H], cpre[H];
-        float xinc = 1.f, xexc = 1.f;
-        if constexpr (INV) {
-            mbar_wait(&bars[slot], parity);
-            lds_row2<T, VPT, FULL>(stage_p(slot) + j0, p_n, umax);
+        // ---- INV(it+1): local chains
+        float2 p_n[H], cpre[H], Dl[H];
+        float xinc = 1.f, einc = 0.f;
+        if (doI) {
+            if (!SOFT) mbar_wait(&bars[slotI], parI);      // with SOFT, MAXS waited for this row one iteration ago
+            lds_row2<T, VPT, FULL>(stage_p(slotI) + j0, p_n, umax);
+            float2 E_n[H];
             if (SOFT) {
                 unsigned dummy = 0u;
-                lds_row2<T, VPT, false>(stage_e(slot) + j0, E_n, dummy);
+                lds_row2<T, VPT, false>(stage_e(slotI) + j0, E_n, dummy);
             }
             if constexpr (!FULL) {
 #pragma unroll
@@ -159,39 +221,104 @@ mma_fwd_pipe_kernel(const MmaParams prm, const StagePlan plan) {
                     if (is_in(k)) bad = bad || !(pk >= -1e-10f) || !(pk <= 1.0f);
                     if (!is_live(k)) pk = 0.f;
                     if (SOFT) {
-                        float& ek = SIMULST_EL(E_n, k);
-                        if (!is_live(k)) ek = is_in(k) ? fill : -INFINITY;
+                        if (!is_live(k)) SIMULST_EL(E_n, k) = is_in(k) ? fill : -INFINITY;
                     }
                 }
             }
-            const float xt = local_cumprod<VPT>(p_n, eps, cpre);
-            xinc = wscan_prefix_mul(xt);
-            if (lane == 31) xA[1 * kXStride + warp] = xinc;
-            xexc = wprev(xinc, 1.f);
+            xinc = local_cumprod<VPT>(p_n, eps, cpre);
             if (SOFT) {
-                float em = fmaxf(E_n[0].x, E_n[0].y);
+                float2 unused[H], ex_n[H];
+                einc = local_exp_prefix<VPT, false>(E_n, m_cur, eps, unused, ex_n, Dl);
+                nan_out = nan_out || (einc != einc);
 #pragma unroll
-                for (int q = 1; q < H; ++q) em = fmaxf(em, fmaxf(E_n[q].x, E_n[q].y));
-                const float wm = wmax_redux(em);
-                if (lane == 0) xA[2 * kXStride + warp] = wm;
+                for (int q = 0; q < VPT / 4; ++q)
+                    stash[(sb_w * (VPT / 4) + q) * THREADS + tid] =
+                        make_float4(ex_n[2 * q].x, ex_n[2 * q].y, ex_n[2 * q + 1].x, ex_n[2 * q + 1].y);
             }
         }
-        __syncthreads();                    // ---- barrier A
-        if constexpr (INV) {
-            // every thread has read ring slot `slot`: refill it with the row NS steps ahead
-            if (tid == 0 && i + 1 + NS < T_len) issue(i + 1 + NS, slot);
-            if (++slot == NS) { slot = 0; parity ^= 1u; }
+        // ---- RECU(it): local u-prefix
+        float2 sl[H];
+        float uinc = 0.f;
+        if (doU) {
+            uinc = local_u_prefix<VPT>(a_prev, rc, sl);
+            nan_out = nan_out || (uinc != uinc);     // NaN anywhere in u poisons the thread total
+        }
+        // ---- warp level: x / e / u prefix scans, r suffix scan (RECR(it-1); its thread totals
+        //      come from the previous POST), row max, row sum
+        float rinc = rt_prev;
+        float xexc, eexc, uexc, rexc;
+        if (SOFT) {
+            wscan_xeur(xinc, einc, uinc, rinc);
+            wneigh_xeur(xinc, einc, uinc, rinc, xexc, eexc, uexc, rexc);
+            const float wm = wmax_redux(em);
+            if (lane == 0) xw[0 * kXStride + warp] = wm;
+            if (lane == 31) xw[2 * kXStride + warp] = einc;
+            if (lane == 0) xw[4 * kXStride + warp] = rinc;
+        } else {
+            wscan_xu(xinc, uinc);
+            xexc = wprev(xinc, 1.f);
+            uexc = wprev(uinc, 0.f);
+            eexc = rexc = 0.f;
+        }
+        if (lane == 31) xw[1 * kXStride + warp] = xinc;
+        if (lane == 31) xw[3 * kXStride + warp] = uinc;
+        if (mp) {
+            const float ws = warp_sum(rsum_prev);
+            if (lane == 0) xw[5 * kXStride + warp] = ws;
         }
 
-        // ================================================= phase B
-        float2 Rl[H];
-        float rexc = 0.f, a_last_raw = 0.f;
-        if constexpr (REC) {
-            const float ubase = xw_prefix_add<NW>(xA + 0 * kXStride, warp, lane) + uexc;
+        __syncthreads();                    // ================================ the barrier
+        // every thread has read ring slot `slotI`: refill it with the row NS steps ahead
+        if (tid == 0 && doI && it + 1 + NS < T_len) issue(it + 1 + NS, slotI);
+        if (++slotI == NS) { slotI = 0; parI ^= 1u; }
+
+        // ================================================================ POST
+        if (SOFT && doM) m_cur = xw_max<NW>(xw + 0 * kXStride, lane);
+        // ---- RECR(it-1): beta, mass-preserved column
+        if (doR) {
+            const int i = it - 1;
+            float resid = 0.f, row_total = 0.f;
+            if (mp) {
+                row_total = xw_sum<NW>(xw + 5 * kXStride, lane);
+                resid = 1.0f - fminf(fmaxf(row_total, 0.0f), 1.0f);
+            }
+            if (SOFT) {
+                // R_k = sum_{q>=k} r_q  (+ resid / D_last for every k <= last; positions beyond
+                // `last` are padded or outside the row, their beta is zero anyway)
+                float rbase = xw_suffix_add<NW>(xw + 4 * kXStride, warp, lane) + rexc;
+                if (mp) rbase += resid * bcast[i & 3];
+                const float2 rb = f2(rbase);
+                int sb_r = sb_w + 1;
+                if (sb_r == kExStash) sb_r = 0;
+                float2 b[H];
+#pragma unroll
+                for (int q = 0; q < VPT / 4; ++q) {
+                    const float4 e4 = stash[(sb_r * (VPT / 4) + q) * THREADS + tid];
+                    b[2 * q] = min2(mul2(f2(e4.x, e4.y), add2(rb, Rl[2 * q])), 1.0f);
+                    b[2 * q + 1] = min2(mul2(f2(e4.z, e4.w), add2(rb, Rl[2 * q + 1])), 1.0f);
+                }
+                if constexpr (!FULL) {
+#pragma unroll
+                    for (int k = 0; k < VPT; ++k)
+                        if (!is_live(k)) SIMULST_EL(b, k) = 0.f;
+                }
+                st_row2_f32<VPT, FULL>(g_beta + (size_t)i * S, j0, S, vec_out, b);
+            }
+            if (own_last) {
+                // the row itself was stored one iteration ago; patch the one column
+                g_alpha[(size_t)i * S + last] = mp_add ? (a_last_raw + resid) : resid;
+                if (prm.side != nullptr)
+                    *reinterpret_cast<float2*>(prm.side + ((size_t)n * T_len + i) * 2) = make_float2(a_last_raw, row_total);
+            }
+        }
+        // ---- RECU(it): alpha_it, thread-local r-suffix / row sum of step it
+        if (doU) {
+            const float ubase = xw_prefix_add<NW>(xw + 3 * kXStride, warp, lane) + uexc;
             float2 sfull[H], z[H];
             finish_u_prefix<VPT>(ubase, sl, P, sfull, z);
 #pragma unroll
             for (int q = 0; q < H; ++q) a_prev[q] = min2(z[q], 1.0f);      // z >= 0: P >= 0, s >= 0
+            st_row2_f32<VPT, FULL>(g_alpha + (size_t)it * S, j0, S, vec_out, a_prev);
             if (mp || SOFT) {
                 // alpha entering the row sum / the soft-attention numerator: the mass-preservation
                 // column is left out when it is REPLACED (its residual is added analytically)
@@ -201,105 +328,46 @@ mma_fwd_pipe_kernel(const MmaParams prm, const StagePlan plan) {
                 if (own_last) {
 #pragma unroll
                     for (int k = 0; k < VPT; ++k)
-                        if ((FULL ? k == VPT - 1 : true) && k == k_last) {
+                        if (at_last(k)) {
                             a_last_raw = SIMULST_EL(a_s, k);
                             if (!mp_add) SIMULST_EL(a_s, k) = 0.f;
                         }
                 }
-                if (SOFT) {
-                    const float rt = local_r_suffix<VPT>(a_s, rD, Rl);
-                    const float rinc = wscan_suffix_add(rt);
-                    if (lane == 0) xB[0 * kXStride + warp] = rinc;
-                    rexc = wnext(rinc, 0.f);
-                }
+                if (SOFT) rt_prev = local_r_suffix<VPT>(a_s, rD, Rl);
                 if (mp) {
                     float2 acc = a_s[0];
 #pragma unroll
                     for (int q = 1; q < H; ++q) acc = add2(acc, a_s[q]);
-                    const float ws = warp_sum(acc.x + acc.y);
-                    if (lane == 0) xB[1 * kXStride + warp] = ws;
+                    rsum_prev = acc.x + acc.y;
                 }
             }
         }
-        float2 ex_n[H], Dl[H], rc_n[H], P_n[H];
-        float eexc = 0.f;
-        if constexpr (INV) {
-            const float xoff = xw_prefix_mul<NW>(xA + 1 * kXStride, warp, lane);
+        // ---- INV(it+1): cp, 1/c, P, 1/D
+        if (doI) {
+            const float xoff = xw_prefix_mul<NW>(xw + 1 * kXStride, warp, lane);
             const float cbase = (one_eps * xoff) * xexc;
             float2 cp[H];
-            finish_cumprod<VPT>(cbase, cpre, p_n, eps, cp, rc_n, P_n);
+            finish_cumprod<VPT>(cbase, cpre, p_n, eps, cp, rc, P);
             if (SOFT) {
-                const float m = xw_max<NW>(xA + 2 * kXStride, lane);
-                float2 unused[H];
-                const float et = local_exp_prefix<VPT, false>(E_n, m, eps, unused, ex_n, Dl);
-                nan_out = nan_out || (et != et);
-                const float einc = wscan_prefix_add(et);
-                if (lane == 31) xB[2 * kXStride + warp] = einc;
-                eexc = wprev(einc, 0.f);
-            }
-        }
-        __syncthreads();                    // ---- barrier B
-
-        // ================================================= phase C
-        if constexpr (REC) {
-            float resid = 0.f, row_total = 0.f;
-            if (mp) {
-                row_total = xw_sum<NW>(xB + 1 * kXStride, lane);
-                resid = 1.0f - fminf(fmaxf(row_total, 0.0f), 1.0f);
-            }
-            if (SOFT) {
-                // R_k = sum_{q>=k} r_q  (+ resid / D_last for every k <= last; positions beyond
-                // `last` are padded or outside the row, their beta is zero anyway)
-                float rbase = xw_suffix_add<NW>(xB + 0 * kXStride, warp, lane) + rexc;
-                if (mp) rbase += resid * bcast[i & 1];
-                const float2 rb = f2(rbase);
-                float2 b[H];
-#pragma unroll
-                for (int q = 0; q < H; ++q) b[q] = min2(mul2(ex[q], add2(rb, Rl[q])), 1.0f);
-                if constexpr (!FULL) {
-#pragma unroll
-                    for (int k = 0; k < VPT; ++k)
-                        if (!is_live(k)) SIMULST_EL(b, k) = 0.f;
-                }
-                st_row2_f32<VPT, FULL>(g_beta + (size_t)i * S, j0, S, vec_out, b);
-            }
-            if (own_last) {
-                float2 a_out[H];
-#pragma unroll
-                for (int q = 0; q < H; ++q) a_out[q] = a_prev[q];
-#pragma unroll
-                for (int k = 0; k < VPT; ++k)
-                    if ((FULL ? k == VPT - 1 : true) && k == k_last)
-                        SIMULST_EL(a_out, k) = mp_add ? (a_last_raw + resid) : resid;
-                st_row2_f32<VPT, FULL>(g_alpha + (size_t)i * S, j0, S, vec_out, a_out);
-                if (prm.side != nullptr)
-                    *reinterpret_cast<float2*>(prm.side + ((size_t)n * T_len + i) * 2) = make_float2(a_last_raw, row_total);
-            } else {
-                st_row2_f32<VPT, FULL>(g_alpha + (size_t)i * S, j0, S, vec_out, a_prev);
-            }
-        }
-        if constexpr (INV) {
-#pragma unroll
-            for (int q = 0; q < H; ++q) { rc[q] = rc_n[q]; P[q] = P_n[q]; }
-            if (SOFT) {
-                const float ebase = xw_prefix_add<NW>(xB + 2 * kXStride, warp, lane) + eexc;
+                const float ebase = xw_prefix_add<NW>(xw + 2 * kXStride, warp, lane) + eexc;
                 finish_exp_prefix<VPT>(ebase, eps, Dl, rD);
-#pragma unroll
-                for (int q = 0; q < H; ++q) ex[q] = ex_n[q];
                 if (own_last) {
 #pragma unroll
                     for (int k = 0; k < VPT; ++k)
-                        if ((FULL ? k == VPT - 1 : true) && k == k_last) bcast[(i + 1) & 1] = SIMULST_EL(rD, k);
+                        if (at_last(k)) bcast[(it + 1) & 3] = SIMULST_EL(rD, k);
                 }
             }
         }
+        if (++sb_w == kExStash) sb_w = 0;
     };
 
-    using Yes = std::integral_constant<bool, true>;
-    using No = std::integral_constant<bool, false>;
-    body(No{}, Yes{}, -1);                                   // prologue: invariants of step 0
-    for (int i = 0; i < T_len - 1; ++i) body(Yes{}, Yes{}, i);
-    body(Yes{}, No{}, T_len - 1);                            // epilogue: last recurrence step
+    using Steady = std::integral_constant<bool, true>;
+    using Edge = std::integral_constant<bool, false>;
+    // iterations -2 .. T_len; all four stages are live for 1 <= it <= T_len - 3
+    int it = -2;
+    for (; it < 1 && it <= T_len; ++it) body(Edge{}, it);
+    for (; it <= T_len - 3; ++it) body(Steady{}, it);
+    for (; it <= T_len; ++it) body(Edge{}, it);
 
     // ---- data-error reporting (prob_check / safe_cumprod semantics), slow path only on error
     if (prm.status != nullptr) {
@@ -320,16 +388,18 @@ mma_fwd_pipe_kernel(const MmaParams prm, const StagePlan plan) {
 }
 
 // ------------------------------------------------------------------ host-side launcher
+// Returns 1 when the row does not fit the pipelined kernel (caller falls back to the generic one).
 template <int THREADS, int VPT, typename T, bool SOFT, bool FULL>
 int launch_mma_fwd_pipe_impl(const MmaParams& prm, cudaStream_t stream) {
-    StagePlan plan;
+    PipePlan plan;
     plan.rows = SOFT ? 2 : 1;
     plan.row_bytes = ((THREADS * VPT * (int)sizeof(T)) + 127) / 128 * 128;
-    plan.win_floats = 0;
+    plan.stash_bytes = SOFT ? kExStash * THREADS * VPT * 4 : 0;
     plan.n_stage = kPipeStages;
     // keep 4 CTAs of a 128-thread configuration resident (<= 56 KB each); long rows: what fits
     const size_t budget = THREADS <= 128 ? 56 * 1024 : (THREADS <= 256 ? 110 * 1024 : 220 * 1024);
     while (plan.n_stage > 1 && plan.total() > budget) --plan.n_stage;
+    if (plan.total() > budget || (SOFT && plan.n_stage < 2)) return 1;
     auto kern = mma_fwd_pipe_kernel<THREADS, VPT, T, SOFT, FULL>;
     static size_t attr_set[64] = {};    // per device: largest dynamic smem size opted into
     int dev = 0;

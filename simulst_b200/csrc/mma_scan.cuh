@@ -38,9 +38,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
 constexpr float kLog2e = 1.4426950408889634f;
 
 // ------------------------------------------------------------------ warp scans (predicated shuffles)
+// The asm statements are `volatile`: a pure asm may be sunk by the compiler into code that only
+// some lanes execute (it then wraps every shuffle in WARPSYNC.COLLECTIVE / ENDCOLLECTIVE).
 template <int D>
 __device__ __forceinline__ void shfl_up_add(float& v) {
-    asm("{\n\t.reg .f32 t;\n\t.reg .pred q;\n\t"
+    asm volatile("{\n\t.reg .f32 t;\n\t.reg .pred q;\n\t"
         "shfl.sync.up.b32 t|q, %0, %1, 0, 0xffffffff;\n\t"
         "@q add.rn.f32 %0, %0, t;\n\t}"
         : "+f"(v)
@@ -48,7 +50,7 @@ __device__ __forceinline__ void shfl_up_add(float& v) {
 }
 template <int D>
 __device__ __forceinline__ void shfl_up_mul(float& v) {
-    asm("{\n\t.reg .f32 t;\n\t.reg .pred q;\n\t"
+    asm volatile("{\n\t.reg .f32 t;\n\t.reg .pred q;\n\t"
         "shfl.sync.up.b32 t|q, %0, %1, 0, 0xffffffff;\n\t"
         "@q mul.rn.f32 %0, %0, t;\n\t}"
         : "+f"(v)
@@ -56,7 +58,7 @@ __device__ __forceinline__ void shfl_up_mul(float& v) {
 }
 template <int D>
 __device__ __forceinline__ void shfl_down_add(float& v) {
-    asm("{\n\t.reg .f32 t;\n\t.reg .pred q;\n\t"
+    asm volatile("{\n\t.reg .f32 t;\n\t.reg .pred q;\n\t"
         "shfl.sync.down.b32 t|q, %0, %1, 31, 0xffffffff;\n\t"
         "@q add.rn.f32 %0, %0, t;\n\t}"
         : "+f"(v)
@@ -75,10 +77,59 @@ __device__ __forceinline__ float wscan_suffix_add(float v) {
     shfl_down_add<1>(v); shfl_down_add<2>(v); shfl_down_add<4>(v); shfl_down_add<8>(v); shfl_down_add<16>(v);
     return v;
 }
+// Fused scans of the pipelined kernels: several independent inclusive scans advance level by
+// level in one asm statement, so their shuffle latencies overlap by construction.
+//   x: prefix product   e, u: prefix sums   r: suffix sum
+template <int D>
+__device__ __forceinline__ void scan_level_xeur(float& x, float& e, float& u, float& r) {
+    asm volatile("{\n\t.reg .f32 t0, t1, t2, t3;\n\t.reg .pred q0, q1;\n\t"
+        "shfl.sync.up.b32 t0|q0, %0, %4, 0, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 t1, %1, %4, 0, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 t2, %2, %4, 0, 0xffffffff;\n\t"
+        "shfl.sync.down.b32 t3|q1, %3, %4, 31, 0xffffffff;\n\t"
+        "@q0 mul.rn.f32 %0, %0, t0;\n\t"
+        "@q0 add.rn.f32 %1, %1, t1;\n\t"
+        "@q0 add.rn.f32 %2, %2, t2;\n\t"
+        "@q1 add.rn.f32 %3, %3, t3;\n\t}"
+        : "+f"(x), "+f"(e), "+f"(u), "+f"(r)
+        : "n"(D));
+}
+__device__ __forceinline__ void wscan_xeur(float& x, float& e, float& u, float& r) {
+    scan_level_xeur<1>(x, e, u, r); scan_level_xeur<2>(x, e, u, r); scan_level_xeur<4>(x, e, u, r);
+    scan_level_xeur<8>(x, e, u, r); scan_level_xeur<16>(x, e, u, r);
+}
+template <int D>
+__device__ __forceinline__ void scan_level_xu(float& x, float& u) {
+    asm volatile("{\n\t.reg .f32 t0, t1;\n\t.reg .pred q0;\n\t"
+        "shfl.sync.up.b32 t0|q0, %0, %2, 0, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 t1, %1, %2, 0, 0xffffffff;\n\t"
+        "@q0 mul.rn.f32 %0, %0, t0;\n\t"
+        "@q0 add.rn.f32 %1, %1, t1;\n\t}"
+        : "+f"(x), "+f"(u)
+        : "n"(D));
+}
+__device__ __forceinline__ void wscan_xu(float& x, float& u) {
+    scan_level_xu<1>(x, u); scan_level_xu<2>(x, u); scan_level_xu<4>(x, u); scan_level_xu<8>(x, u); scan_level_xu<16>(x, u);
+}
+// neighbours of the four inclusive results: previous lane for x / e / u (identity 1 / 0 / 0 at
+// lane 0), next lane for r (0 at lane 31)
+__device__ __forceinline__ void wneigh_xeur(float x, float e, float u, float r, float& xp, float& ep, float& up, float& rn) {
+    asm volatile("{\n\t.reg .pred q0, q1;\n\t"
+        "shfl.sync.up.b32 %0|q0, %4, 1, 0, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 %1, %5, 1, 0, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 %2, %6, 1, 0, 0xffffffff;\n\t"
+        "shfl.sync.down.b32 %3|q1, %7, 1, 31, 0xffffffff;\n\t"
+        "@!q0 mov.f32 %0, 0f3F800000;\n\t"
+        "@!q0 mov.f32 %1, 0f00000000;\n\t"
+        "@!q0 mov.f32 %2, 0f00000000;\n\t"
+        "@!q1 mov.f32 %3, 0f00000000;\n\t}"
+        : "=&f"(xp), "=&f"(ep), "=&f"(up), "=&f"(rn)
+        : "f"(x), "f"(e), "f"(u), "f"(r));
+}
 // value of the previous / next lane, `ident` at the warp edge
 __device__ __forceinline__ float wprev(float v, float ident) {
     float o;
-    asm("{\n\t.reg .pred q;\n\t"
+    asm volatile("{\n\t.reg .pred q;\n\t"
         "shfl.sync.up.b32 %0|q, %1, 1, 0, 0xffffffff;\n\t"
         "@!q mov.f32 %0, %2;\n\t}"
         : "=&f"(o)
@@ -87,7 +138,7 @@ __device__ __forceinline__ float wprev(float v, float ident) {
 }
 __device__ __forceinline__ float wnext(float v, float ident) {
     float o;
-    asm("{\n\t.reg .pred q;\n\t"
+    asm volatile("{\n\t.reg .pred q;\n\t"
         "shfl.sync.down.b32 %0|q, %1, 1, 31, 0xffffffff;\n\t"
         "@!q mov.f32 %0, %2;\n\t}"
         : "=&f"(o)

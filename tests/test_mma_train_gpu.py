@@ -137,18 +137,44 @@ def test_mma_train_matches_oracle(n, t, s, masked, chunk, cfg):
 
 
 def test_tma_and_cooperative_staging_agree():
+    """Generic kernels: rows staged by TMA bulk copies or by cooperative loads give the same bits."""
     from simulst_b200 import _lib
     lib = _lib.load()
     p, se, mask, ga, gb = _seeded(3, 9, 512, seed=5, masked=True)
     outs = []
-    for tma in (1, 0):
-        lib.simulst_mma_set_tma(tma)
-        try:
+    lib.simulst_mma_set_pipeline(0)
+    try:
+        for tma in (1, 0):
+            lib.simulst_mma_set_tma(tma)
             outs.append(_run(p, se, mask, True, 0, True, ga, gb))
-        finally:
-            lib.simulst_mma_set_tma(1)
+    finally:
+        lib.simulst_mma_set_tma(1)
+        lib.simulst_mma_set_pipeline(1)
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("masked", [False, True])
+@pytest.mark.parametrize("soft", [False, True])
+def test_pipelined_and_generic_kernels_agree(masked, soft):
+    """The software-pipelined kernels and the generic (one scan per barrier) kernels evaluate the
+    same formulas with different scan groupings: results agree to a few ulp of the row scale."""
+    from simulst_b200 import _lib
+    lib = _lib.load()
+    p, se, mask, ga, gb = _seeded(3, 17, 1024, seed=11, masked=masked)
+    outs = []
+    try:
+        for pipe in (1, 0):
+            lib.simulst_mma_set_pipeline(pipe)
+            outs.append(_run(p, se if soft else None, mask, True, 0, True, ga, gb if soft else None))
+    finally:
+        lib.simulst_mma_set_pipeline(1)
+    for a, b in zip(*outs):
+        if a is None:
+            assert b is None
+            continue
+        scale = float(b.abs().max())
+        torch.testing.assert_close(a, b, rtol=2e-6, atol=2e-6 * scale)
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
