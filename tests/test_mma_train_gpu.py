@@ -166,7 +166,7 @@ def test_pipelined_and_generic_kernels_agree(masked, soft):
     try:
         for pipe in (1, 0):
             lib.simulst_mma_set_pipeline(pipe)
-            outs.append(_run(p, se if soft else None, mask, True, 0, True, ga, gb if soft else None))
+            outs.append(_run(p, se if soft else None, mask, True, 0, soft, ga, gb if soft else None))
     finally:
         lib.simulst_mma_set_pipeline(1)
     for a, b in zip(*outs):
