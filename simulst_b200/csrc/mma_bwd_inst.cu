@@ -1,6 +1,8 @@
 // Instantiations of the MMA backward kernel for ONE activation dtype (selected with
 // -DSIMULST_INST_DTYPE=0|1|2 so the three dtypes compile in parallel).
 #include "mma_bwd.cuh"
+#include "mma_bwd_pipe.cuh"
+#include "mma_fwd_pipe.cuh"
 #include "mma_dispatch.h"
 
 namespace simulst {
@@ -19,6 +21,13 @@ using InstT = __half;
 int INST_NAME(const MmaParams& prm, int mode, int threads, int vpt, cudaStream_t stream) {
 #define X(TH, VP)                                                                         \
     if (threads == TH && vpt == VP) {                                                     \
+        if constexpr (TH <= kPipeMaxThreads) {                                            \
+            if (prm.tma && prm.pipe && mode != kModeSoftCk) {                             \
+                const int rc = mode == kModeHard ? launch_mma_bwd_pipe<TH, VP, InstT, false>(prm, stream) \
+                                                 : launch_mma_bwd_pipe<TH, VP, InstT, true>(prm, stream); \
+                if (rc != 1) return rc;         /* 1 = row too long for the pipelined kernel */ \
+            }                                                                             \
+        }                                                                                 \
         switch (mode) {                                                                   \
             case kModeHard: return launch_mma_bwd<TH, VP, InstT, kModeHard>(prm, stream); \
             case kModeSoftIL: return launch_mma_bwd<TH, VP, InstT, kModeSoftIL>(prm, stream); \

@@ -156,7 +156,7 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
     unsigned parI = 1u;
     int sb_w = kExStash - 1;                // exp-stash buffer of step it+1 (INV writes it); RECR(it-1) reads the next one
 
-    auto body = [&](auto steady_c, const int it) {
+    auto body = [&](auto steady_c, const int it) __attribute__((always_inline)) {
         constexpr bool STEADY = decltype(steady_c)::value;
         const bool doM = SOFT && (STEADY || it + 2 < T_len);
         const bool doI = STEADY || (it >= -1 && it + 1 < T_len);

@@ -126,6 +126,98 @@ __device__ __forceinline__ void wneigh_xeur(float x, float e, float u, float r, 
         : "=&f"(xp), "=&f"(ep), "=&f"(up), "=&f"(rn)
         : "f"(x), "f"(e), "f"(u), "f"(r));
 }
+// ---- backward kernel, barrier 1: x prefix product, e prefix sum, q prefix sum (only its
+// total at lane 31 is used), g suffix sum
+template <int D>
+__device__ __forceinline__ void scan_level_b1(float& x, float& e, float& q, float& g) {
+    asm volatile("{\n\t.reg .f32 t0, t1, t2, t3;\n\t.reg .pred q0, q1;\n\t"
+        "shfl.sync.up.b32 t0|q0, %0, %4, 0, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 t1, %1, %4, 0, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 t2, %2, %4, 0, 0xffffffff;\n\t"
+        "shfl.sync.down.b32 t3|q1, %3, %4, 31, 0xffffffff;\n\t"
+        "@q0 mul.rn.f32 %0, %0, t0;\n\t"
+        "@q0 add.rn.f32 %1, %1, t1;\n\t"
+        "@q0 add.rn.f32 %2, %2, t2;\n\t"
+        "@q1 add.rn.f32 %3, %3, t3;\n\t}"
+        : "+f"(x), "+f"(e), "+f"(q), "+f"(g)
+        : "n"(D));
+}
+__device__ __forceinline__ void wscan_b1(float& x, float& e, float& q, float& g) {
+    scan_level_b1<1>(x, e, q, g); scan_level_b1<2>(x, e, q, g); scan_level_b1<4>(x, e, q, g);
+    scan_level_b1<8>(x, e, q, g); scan_level_b1<16>(x, e, q, g);
+}
+// neighbours: previous lane of x (1 at lane 0) and e (0), next lane of g (0 at lane 31)
+__device__ __forceinline__ void wneigh_b1(float x, float e, float g, float& xp, float& ep, float& gn) {
+    asm volatile("{\n\t.reg .pred q0, q1;\n\t"
+        "shfl.sync.up.b32 %0|q0, %3, 1, 0, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 %1, %4, 1, 0, 0xffffffff;\n\t"
+        "shfl.sync.down.b32 %2|q1, %5, 1, 31, 0xffffffff;\n\t"
+        "@!q0 mov.f32 %0, 0f3F800000;\n\t"
+        "@!q0 mov.f32 %1, 0f00000000;\n\t"
+        "@!q1 mov.f32 %2, 0f00000000;\n\t}"
+        : "=&f"(xp), "=&f"(ep), "=&f"(gn)
+        : "f"(x), "f"(e), "f"(g));
+}
+// ---- backward kernel, barrier 2: u prefix sum; R, W, L suffix sums
+template <int D>
+__device__ __forceinline__ void scan_level_b2(float& u, float& r, float& w, float& l) {
+    asm volatile("{\n\t.reg .f32 t0, t1, t2, t3;\n\t.reg .pred q0, q1;\n\t"
+        "shfl.sync.up.b32 t0|q0, %0, %4, 0, 0xffffffff;\n\t"
+        "shfl.sync.down.b32 t1|q1, %1, %4, 31, 0xffffffff;\n\t"
+        "shfl.sync.down.b32 t2, %2, %4, 31, 0xffffffff;\n\t"
+        "shfl.sync.down.b32 t3, %3, %4, 31, 0xffffffff;\n\t"
+        "@q0 add.rn.f32 %0, %0, t0;\n\t"
+        "@q1 add.rn.f32 %1, %1, t1;\n\t"
+        "@q1 add.rn.f32 %2, %2, t2;\n\t"
+        "@q1 add.rn.f32 %3, %3, t3;\n\t}"
+        : "+f"(u), "+f"(r), "+f"(w), "+f"(l)
+        : "n"(D));
+}
+__device__ __forceinline__ void wscan_b2(float& u, float& r, float& w, float& l) {
+    scan_level_b2<1>(u, r, w, l); scan_level_b2<2>(u, r, w, l); scan_level_b2<4>(u, r, w, l);
+    scan_level_b2<8>(u, r, w, l); scan_level_b2<16>(u, r, w, l);
+}
+__device__ __forceinline__ void wneigh_b2(float u, float r, float w, float l, float& up, float& rn, float& wn, float& ln) {
+    asm volatile("{\n\t.reg .pred q0, q1;\n\t"
+        "shfl.sync.up.b32 %0|q0, %4, 1, 0, 0xffffffff;\n\t"
+        "shfl.sync.down.b32 %1|q1, %5, 1, 31, 0xffffffff;\n\t"
+        "shfl.sync.down.b32 %2, %6, 1, 31, 0xffffffff;\n\t"
+        "shfl.sync.down.b32 %3, %7, 1, 31, 0xffffffff;\n\t"
+        "@!q0 mov.f32 %0, 0f00000000;\n\t"
+        "@!q1 mov.f32 %1, 0f00000000;\n\t"
+        "@!q1 mov.f32 %2, 0f00000000;\n\t"
+        "@!q1 mov.f32 %3, 0f00000000;\n\t}"
+        : "=&f"(up), "=&f"(rn), "=&f"(wn), "=&f"(ln)
+        : "f"(u), "f"(r), "f"(w), "f"(l));
+}
+// ---- one prefix sum + one suffix sum (backward barrier 3: gr / V; hard-mode barriers)
+template <int D>
+__device__ __forceinline__ void scan_level_ud(float& u, float& d) {
+    asm volatile("{\n\t.reg .f32 t0, t1;\n\t.reg .pred q0, q1;\n\t"
+        "shfl.sync.up.b32 t0|q0, %0, %2, 0, 0xffffffff;\n\t"
+        "shfl.sync.down.b32 t1|q1, %1, %2, 31, 0xffffffff;\n\t"
+        "@q0 add.rn.f32 %0, %0, t0;\n\t"
+        "@q1 add.rn.f32 %1, %1, t1;\n\t}"
+        : "+f"(u), "+f"(d)
+        : "n"(D));
+}
+__device__ __forceinline__ void wscan_ud(float& u, float& d) {
+    scan_level_ud<1>(u, d); scan_level_ud<2>(u, d); scan_level_ud<4>(u, d); scan_level_ud<8>(u, d); scan_level_ud<16>(u, d);
+}
+// prefix product + suffix sum (hard-mode backward barrier 1)
+template <int D>
+__device__ __forceinline__ void scan_level_xd(float& x, float& d) {
+    asm volatile("{\n\t.reg .f32 t0, t1;\n\t.reg .pred q0, q1;\n\t"
+        "shfl.sync.up.b32 t0|q0, %0, %2, 0, 0xffffffff;\n\t"
+        "shfl.sync.down.b32 t1|q1, %1, %2, 31, 0xffffffff;\n\t"
+        "@q0 mul.rn.f32 %0, %0, t0;\n\t"
+        "@q1 add.rn.f32 %1, %1, t1;\n\t}"
+        : "+f"(x), "+f"(d)
+        : "n"(D));
+}
+__device__ __forceinline__ void wscan_xd(float& x, float& d) {
+    scan_level_xd<1>(x, d); scan_level_xd<2>(x, d); scan_level_xd<4>(x, d); scan_level_xd<8>(x, d); scan_level_xd<16>(x, d);
+}
 // value of the previous / next lane, `ident` at the warp edge
 __device__ __forceinline__ float wprev(float v, float ident) {
     float o;
