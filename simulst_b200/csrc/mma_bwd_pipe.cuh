@@ -39,9 +39,9 @@ struct BwdPipePlan {
     int soft;
     int stash_bytes;   // 5 arrays * THREADS * VPT * 4
     __host__ __device__ int header_bytes() const { return 128 + kBwdSlots * kXStride * 4 + 128; }
-    // p ring (3) [+ energy ring (3)] + alpha ring (2) + stash
+    // p ring (3) [+ energy ring (3)] + alpha ring (3) + stash
     __host__ __device__ size_t total() const {
-        return (size_t)header_bytes() + (size_t)(soft ? 6 : 3) * row_t_bytes + (size_t)2 * row_f_bytes + (size_t)stash_bytes;
+        return (size_t)header_bytes() + (size_t)(soft ? 6 : 3) * row_t_bytes + (size_t)3 * row_f_bytes + (size_t)stash_bytes;
     }
 };
 
@@ -54,13 +54,13 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
     static_assert(VPT % 4 == 0, "VPT must be a multiple of 4");
 
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);       // [0..2] p ring, [3..5] energy ring, [6..7] alpha ring
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);       // [0..2] p ring, [3..5] energy ring, [6..8] alpha ring
     float* xb = reinterpret_cast<float*>(smem + 128);         // [kBwdSlots][32]
     float* bcast = xb + kBwdSlots * kXStride;                 // [0] 1/D at the mass-preservation column
     unsigned char* ring_p = smem + plan.header_bytes();
     unsigned char* ring_e = ring_p + 3 * plan.row_t_bytes;
     unsigned char* ring_a = ring_e + (SOFT ? 3 * plan.row_t_bytes : 0);
-    float4* stash = reinterpret_cast<float4*>(ring_a + 2 * plan.row_f_bytes);
+    float4* stash = reinterpret_cast<float4*>(ring_a + 3 * plan.row_f_bytes);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = blockIdx.x;
@@ -103,7 +103,7 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
     int last = S - 1;
 
     if (tid == 0) {
-        for (int b = 0; b < 8; ++b) mbar_init(&bars[b], 1);
+        for (int b = 0; b < 9; ++b) mbar_init(&bars[b], 1);
         mbar_fence_init();
     }
     if (mp_add) {
@@ -128,9 +128,8 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
     const unsigned t_bytes = (unsigned)(S * sizeof(T)), f_bytes = (unsigned)(S * 4);
     auto slot_p = [&](int k3) { return reinterpret_cast<const T*>(ring_p + (size_t)k3 * plan.row_t_bytes); };
     auto slot_e = [&](int k3) { return reinterpret_cast<const T*>(ring_e + (size_t)k3 * plan.row_t_bytes); };
-    auto slot_a = [&](int k2) { return reinterpret_cast<const float*>(ring_a + (size_t)k2 * plan.row_f_bytes); };
-    // thread 0 only.  Row r of p / energy goes to ring position (T-1-r) % 3; alpha row r (needed by
-    // step r+1) to position (T-2-r) % 2.
+    auto slot_a = [&](int k3) { return reinterpret_cast<const float*>(ring_a + (size_t)k3 * plan.row_f_bytes); };
+    // thread 0 only.  Row r of p / energy / alpha goes to ring position (T-1-r) % 3.
     auto issue_p = [&](int r) {
         const int k = (T_len - 1 - r) % 3;
         mbar_expect_tx(&bars[k], t_bytes);
@@ -142,7 +141,7 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
         tma_load_1d(const_cast<T*>(slot_e(k)), ge_in + (size_t)r * S, t_bytes, &bars[3 + k]);
     };
     auto issue_a = [&](int r) {
-        const int k = (T_len - 2 - r) % 2;
+        const int k = (T_len - 1 - r) % 3;
         mbar_expect_tx(&bars[6 + k], f_bytes);
         tma_load_1d(const_cast<float*>(slot_a(k)), al + (size_t)r * S, f_bytes, &bars[6 + k]);
     };
@@ -152,31 +151,24 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
             issue_e(T_len - 1);
             if (T_len >= 2) issue_e(T_len - 2);
         }
+        issue_a(T_len - 1);
         if (T_len >= 2) issue_a(T_len - 2);
     }
 
     const float one_eps = 1.0f + eps;
     // ---- state carried between iterations
     float2 carry[H];            // dL/d alpha_{s+1} flowing into LATE(s+1)
-    float2 a_cur[H];            // alpha'_s exactly as stored (EARLY(s): numerator of r)
 #pragma unroll
     for (int q = 0; q < H; ++q) carry[q] = f2(0.f);
-    if (SOFT) {
-        float a8[VPT];
-        ld_row_f32<VPT>(al + (size_t)(T_len - 1) * S, j0, S, vec, a8);
-#pragma unroll
-        for (int q = 0; q < H; ++q) a_cur[q] = f2(a8[2 * q], a8[2 * q + 1]);
-    }
     float m_cur = 0.f;          // row max / arg-max of step s (from MAXS one iteration earlier)
     int amax_cur = -1;
     float gEsum_prev = 0.f;     // thread-local sum of gE*(e-eps) of step s+1, reduced at B1
     float gEm_fix = 0.f;        // this thread's value at the arg-max column of step s+1 (if it owns it)
     int fix_col = -1;
-    // consumption-order ring positions / parities of the rows EARLY(s) reads
-    int kp = 0;                 // p / energy row s: position (T-1-s) % 3
+    // consumption-order ring position / parity of row s (p, energy, alpha alike): (T-1-s) % 3;
+    // row s-1 sits one position further, row s+1 one before
+    int kp = 0;
     unsigned par3 = 0u;
-    int ka = 0;                 // alpha row s-1: position (T-1-s) % 2
-    unsigned par2 = 0u;
 
     auto stash_ld = [&](int arr, float2 (&v)[H]) {
 #pragma unroll
@@ -208,15 +200,17 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
         const bool doM = SOFT && (STEADY || (s - 1 >= 0 && s - 1 < T_len));
         const bool doE = STEADY || (s >= 0 && s < T_len);
         const bool doL = STEADY || (s + 1 >= 0 && s + 1 < T_len);
+        int km = kp + 1;                    // ring position / parity of row s-1
+        unsigned parm = par3;
+        if (km == 3) { km = 0; parm ^= 1u; }
+        int kl = kp - 1;                    // ring position of row s+1
+        if (kl < 0) kl = 2;
 
         // ================================================================ PRE-B1
         // ---- MAXS(s-1): row max and first arg-max of the energies
         float wm = -INFINITY;
         int wcand = 0x7fffffff;
         if (SOFT && doM) {
-            int km = kp + 1;
-            unsigned parm = par3;
-            if (km == 3) { km = 0; parm ^= 1u; }
             mbar_wait(&bars[3 + km], parm);
             float2 Em[H];
             unsigned dummy = 0u;
@@ -237,7 +231,7 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
             wcand = __reduce_min_sync(kFull, cand);
         }
         // ---- EARLY(s) S1: thread-local cumprod and exp prefix
-        float2 p_s[H], cpre[H], ex[H], exm[H], Dl[H];
+        float2 p_s[H], cpre[H], ex[H], Dl[H];
         float xinc = 1.f, einc = 0.f;
         if (doE) {
             mbar_wait(&bars[kp], par3);
@@ -255,7 +249,10 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
                 }
             }
             xinc = local_cumprod<VPT>(p_s, eps, cpre);
-            if (SOFT) einc = local_exp_prefix<VPT, true>(E_s, m_cur, eps, exm, ex, Dl);
+            if (SOFT) {
+                float2 unused[H];
+                einc = local_exp_prefix<VPT, false>(E_s, m_cur, eps, unused, ex, Dl);
+            }
         }
         // ---- LATE(s+1) S5: g0 = g'' + carry, thread-local suffix of mz*P*g0
         float2 g0[H], Al[H];
@@ -310,27 +307,25 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
             const float gEall = xw_sum<NW>(xb + 3 * kXStride, lane);
             if (fix_col >= 0) ge_out[(size_t)(s + 1) * S + fix_col] = from_f32<T>(gEm_fix - gEall);
         }
-        // ---- LATE(s+1): gu, carry', thread-local exclusive suffix of gA = g0*c1 - gu*c2
-        float2 gAl[H];
+        // ---- LATE(s+1): gu, carry', h = g0*c3, thread-local exclusive suffix of gA = g0*c1 - gu*c2
+        float2 hL[H], gAl[H];
         float linc = 0.f;
         if (doL) {
             const float gbase = xw_suffix_add<NW>(xb + 2 * kXStride, warp, lane) + gexc;
             const float2 gb2 = f2(gbase);
-            float2 gu[H], rcL[H], c2[H], c3[H], pL[H];
+            float2 rcL[H], c2[H], c3[H], pL[H];
             stash_ld(2, rcL);
             stash_ld(3, c2);
             stash_ld(4, c3);
-            int kl = kp - 1;                // p row s+1 sits one ring position before row s
-            if (kl < 0) kl = 2;
             unsigned dummy = 0u;
             lds_row2<T, VPT, false>(slot_p(kl) + j0, pL, dummy);
             float2 gAk[H];
 #pragma unroll
             for (int q = 0; q < H; ++q) {
-                gu[q] = add2(gb2, Al[q]);
-                carry[q] = mul2(gu[q], rcL[q]);
-                const float2 c1 = mul2(c3[q], pL[q]);
-                gAk[q] = fma2(g0[q], c1, mul2(mul2(gu[q], c2[q]), f2(-1.f)));
+                const float2 gu = add2(gb2, Al[q]);
+                carry[q] = mul2(gu, rcL[q]);
+                hL[q] = mul2(g0[q], c3[q]);
+                gAk[q] = fma2(hL[q], pL[q], mul2(mul2(gu, c2[q]), f2(-1.f)));      // c1 = c3 * p
             }
             float lt = 0.f;
 #pragma unroll
@@ -340,12 +335,52 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
             }
             linc = lt;
         }
-        // ---- EARLY(s) S1 finish: cp, 1/c, P ; 1/D ; then the alpha rows
-        float2 cp[H], rc[H], P[H], rD[H], am1[H], gB[H];
+        // ---- EARLY(s) S1 finish: cp, 1/c, P ; 1/D ; alpha_{s-1} ; c2.  rc and c2 go to the stash in
+        //      their final form, cp and P are parked there until the z mask is known (POST-B2);
+        //      LATE(s+1) has just read its own copies above.
+        float2 rD[H], gB[H], sl[H], Rl[H], Wl[H];
+        float uinc = 0.f, rinc = 0.f, winc = 0.f;
         if (doE) {
             const float xoff = xw_prefix_mul<NW>(xb + 0 * kXStride, warp, lane);
             const float cbase = (one_eps * xoff) * xexc;
+            float2 cp[H], rc[H], P[H], am1[H];
             finish_cumprod<VPT>(cbase, cpre, p_s, eps, cp, rc, P);
+            stash_st(1, P);
+            stash_st(2, rc);
+            stash_st(4, cp);
+            if (s > 0) {
+                mbar_wait(&bars[6 + km], parm);
+                unsigned dummy = 0u;
+                lds_row2<float, VPT, false>(slot_a(km) + j0, am1, dummy);
+                if constexpr (!FULL) {
+#pragma unroll
+                    for (int k = 0; k < VPT; ++k)
+                        if (!is_in(k)) SIMULST_EL(am1, k) = 0.f;
+                }
+                // undo mass preservation on the stored row: the recurrence ran on the raw alpha
+                if (own_last) {
+                    const float raw = side[2 * (s - 1)];
+#pragma unroll
+                    for (int k = 0; k < VPT; ++k)
+                        if (at_last(k)) SIMULST_EL(am1, k) = raw;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < H; ++q) am1[q] = make_float2((j0 + 2 * q == 0) ? 1.0f : 0.0f, 0.0f);
+            }
+            // ============================================================ PRE-B2 (EARLY S2 local)
+            uinc = local_u_prefix<VPT>(am1, rc, sl);
+            {
+                float2 c2[H];
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) {
+                    const float cpk = SIMULST_EL(cp, k), rck = SIMULST_EL(rc, k);
+                    const bool pass = cpk >= eps && cpk <= 1.0f;
+                    const float u = SIMULST_EL(am1, k) * rck;
+                    SIMULST_EL(c2, k) = pass ? (rck * u) * cpk : 0.f;
+                }
+                stash_st(3, c2);
+            }
             if (SOFT) {
                 const float ebase = xw_prefix_add<NW>(xb + 1 * kXStride, warp, lane) + eexc;
                 finish_exp_prefix<VPT>(ebase, eps, Dl, rD);
@@ -355,39 +390,15 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
                         if (at_last(k)) bcast[0] = SIMULST_EL(rD, k);
                 }
                 ldg_row(gB_in, has_gb, s, gB);
-            }
-            if (s > 0) {
-                mbar_wait(&bars[6 + ka], par2);
-                unsigned dummy = 0u;
-                lds_row2<float, VPT, false>(slot_a(ka) + j0, am1, dummy);
-                if constexpr (!FULL) {
-#pragma unroll
-                    for (int k = 0; k < VPT; ++k)
-                        if (!is_in(k)) SIMULST_EL(am1, k) = 0.f;
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < H; ++q) am1[q] = make_float2((j0 + 2 * q == 0) ? 1.0f : 0.0f, 0.0f);
-            }
-        }
-        // ================================================================ PRE-B2
-        float2 sl[H], Rl[H], Wl[H], a_save[H];
-        float uinc = 0.f, rinc = 0.f, winc = 0.f;
-        if (doE) {
-#pragma unroll
-            for (int q = 0; q < H; ++q) a_save[q] = am1[q];
-            // undo mass preservation on the stored row: the recurrence ran on the raw alpha
-            if (own_last && s > 0) {
-                const float raw = side[2 * (s - 1)];
-#pragma unroll
-                for (int k = 0; k < VPT; ++k)
-                    if (at_last(k)) SIMULST_EL(am1, k) = raw;
-            }
-            uinc = local_u_prefix<VPT>(am1, rc, sl);
-            if (SOFT) {
+                // r = alpha'_s / D with alpha'_s (the row as stored) still in the ring
+                if (s == T_len - 1) mbar_wait(&bars[6 + kp], par3);
                 float2 r[H];
+                {
+                    unsigned dummy = 0u;
+                    lds_row2<float, VPT, false>(slot_a(kp) + j0, r, dummy);
+                }
 #pragma unroll
-                for (int q = 0; q < H; ++q) r[q] = mul2(a_cur[q], rD[q]);
+                for (int q = 0; q < H; ++q) r[q] = mul2(r[q], rD[q]);
                 if constexpr (!FULL) {
 #pragma unroll
                     for (int k = 0; k < VPT; ++k)
@@ -425,10 +436,7 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
         if (doL) {
             const float lbase = xw_suffix_add<NW>(xb + 9 * kXStride, warp, lane) + lexc;
             const float2 lb = f2(lbase);
-            float2 c3[H], pL[H], outp[H];
-            stash_ld(4, c3);
-            int kl = kp - 1;
-            if (kl < 0) kl = 2;
+            float2 pL[H], outp[H];
             unsigned dummy = 0u;
             lds_row2<T, VPT, false>(slot_p(kl) + j0, pL, dummy);
             if constexpr (!FULL) {
@@ -441,38 +449,34 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
             for (int q = 0; q < H; ++q) {
                 const float2 rx = rcp2(add2(fma2(pL[q], neg, one), e2));
                 const float2 gL = add2(lb, gAl[q]);
-                outp[q] = fma2(g0[q], c3[q], mul2(mul2(gL, rx), neg));
+                outp[q] = fma2(mul2(gL, rx), neg, hL[q]);
             }
             float o8[VPT];
 #pragma unroll
             for (int k = 0; k < VPT; ++k) o8[k] = is_live(k) ? SIMULST_EL(outp, k) : 0.f;
             st_row_t<T, VPT, FULL>(gp_out + (size_t)(s + 1) * S, j0, S, vec, o8);
         }
-        // ---- EARLY(s) S2 finish: s, z mask, hand-over coefficients ; R, W, gb, gR
-        float2 gR[H], ge1[H], W[H], gA[H];
+        // ---- EARLY(s) S2 finish: s, z mask -> final mz*P and c3 in the stash ; R, W, gb, gR
+        float2 gR[H], ge1[H], W[H], gA[H], exm[H];
         float gA_last = 0.f;
         if (doE) {
             const float ubase = xw_prefix_add<NW>(xb + 6 * kXStride, warp, lane) + uexc;
-            float2 sfull[H], z[H], Pm[H], c2[H], c3[H];
+            float2 P[H], cp[H], sfull[H], z[H];
+            stash_ld(1, P);
+            stash_ld(4, cp);
             finish_u_prefix<VPT>(ubase, sl, P, sfull, z);
 #pragma unroll
             for (int k = 0; k < VPT; ++k) {
                 const bool inside = SIMULST_EL(z, k) <= 1.0f;                    // z >= 0 (P >= 0, s >= 0)
-                SIMULST_EL(Pm, k) = inside ? SIMULST_EL(P, k) : 0.f;
-                const float sm = inside ? SIMULST_EL(sfull, k) : 0.f;
-                const float cpk = SIMULST_EL(cp, k);
-                SIMULST_EL(c3, k) = sm * cpk;
-                const bool pass = cpk >= eps && cpk <= 1.0f;
-                const float u = SIMULST_EL(am1, k) * SIMULST_EL(rc, k);
-                SIMULST_EL(c2, k) = pass ? (SIMULST_EL(rc, k) * u) * cpk : 0.f;
+                if (!inside) SIMULST_EL(P, k) = 0.f;                             // mz * P
+                SIMULST_EL(cp, k) = inside ? SIMULST_EL(sfull, k) * SIMULST_EL(cp, k) : 0.f;   // c3 = mz * s * cp
             }
-            stash_st(1, Pm);
-            stash_st(2, rc);
-            stash_st(3, c2);
-            stash_st(4, c3);
+            stash_st(1, P);
+            stash_st(4, cp);
             if (SOFT) {
                 const float2 rb = f2(xw_suffix_add<NW>(xb + 7 * kXStride, warp, lane) + rexc);
                 const float2 wb = f2(xw_suffix_add<NW>(xb + 8 * kXStride, warp, lane) + wexc);
+                const float2 me = f2(-eps);
 #pragma unroll
                 for (int q = 0; q < H; ++q) {
                     const float2 R = add2(rb, Rl[q]);
@@ -487,6 +491,7 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
                     }
                     ge1[q] = mul2(gb, R);
                     gR[q] = mul2(gb, ex[q]);
+                    exm[q] = add2(ex[q], me);                                    // exp(E - m) up to an ulp of e
                 }
             }
             ldg_row(gA_in, has_ga, s, gA);
@@ -529,7 +534,8 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
                     const float ok = (row_total >= 0.0f && row_total <= 1.0f) ? 1.0f : 0.0f;
                     okg = ok * (gA_last + gtotal * bcast[0]);
                 }
-                float gEm[VPT], gpp[VPT];
+                float gEm[VPT];
+                float2 g2[H];
                 float gsum = 0.f;
                 gEm_fix = 0.f;
                 fix_col = -1;
@@ -546,16 +552,11 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
                     if (j0 + k == amax_cur) { gEm_fix = gEm[k]; fix_col = j0 + k; }
                     float g = live ? (SIMULST_EL(gA, k) + gsoft) - okg : 0.f;
                     if (mp && !mp_add && at_last(k)) g = 0.f;      // replaced column
-                    gpp[k] = g;
+                    SIMULST_EL(g2, k) = g;
                 }
                 gEsum_prev = gsum;
                 st_row_t<T, VPT, FULL>(ge_out + (size_t)s * S, j0, S, vec, gEm);
-                float2 g2[H];
-#pragma unroll
-                for (int q = 0; q < H; ++q) g2[q] = f2(gpp[2 * q], gpp[2 * q + 1]);
                 stash_st(0, g2);
-#pragma unroll
-                for (int q = 0; q < H; ++q) a_cur[q] = a_save[q];
             }
         } else {
             if (doE) {
@@ -577,14 +578,14 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
             __syncthreads();                // ring slots below must not be refilled while still read
         }
 
-        // ---- ring refills (every read of this iteration's rows is behind the last barrier)
+        // ---- ring refills (every read of this iteration's rows is behind the last barrier):
+        //      rows s (energy, alpha) and s+1 (p) are dead
         if (tid == 0) {
             if (SOFT && s - 3 >= 0) issue_e(s - 3);
             if (s - 2 >= 0) issue_p(s - 2);
             if (s - 3 >= 0) issue_a(s - 3);
         }
         if (++kp == 3) { kp = 0; par3 ^= 1u; }
-        if (++ka == 2) { ka = 0; par2 ^= 1u; }
         if (SOFT && doM) { m_cur = m_nxt; amax_cur = amax_nxt; }
     };
 
@@ -592,7 +593,7 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
     using Edge = std::integral_constant<bool, false>;
     // s = T_len (MAXS only) ... -1 (LATE only); all stages are live for 1 <= s <= T_len - 2.
     // Ring positions are counted from s = T_len - 1, so the first iteration starts one before.
-    kp = 2; par3 = 1u; ka = 1; par2 = 1u;
+    kp = 2; par3 = 1u;
     int s = T_len;
     for (; s > T_len - 2 && s >= -1; --s) body(Edge{}, s);
     for (; s >= 1; --s) body(Steady{}, s);
