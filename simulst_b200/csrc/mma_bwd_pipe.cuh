@@ -22,8 +22,10 @@
 //   B2: u-prefix, R-suffix, W-suffix, gL-suffix
 //   B3: gr-prefix, V-suffix
 // EARLY hands {g'', mz*P, rc, c2, c3} to LATE through a thread-private shared-memory stash.
-// Rows of p / energy / alpha arrive through TMA rings (UBLKCP); grad_alpha / grad_beta are
-// read straight from global memory one barrier ahead of their use.
+// Every global read is a TMA 1-D bulk copy (UBLKCP) issued a step ahead by one thread: rings
+// for p / energy / alpha (3 deep: a row is visited by two consecutive iterations), a single
+// slot for grad_beta, and grad_alpha lands directly in the (double-buffered) g'' slot of the
+// stash, where EARLY turns it into g'' in place.
 #pragma once
 
 #include "mma_common.cuh"
@@ -37,11 +39,12 @@ struct BwdPipePlan {
     int row_t_bytes;   // bytes reserved per staged p / energy row (multiple of 128)
     int row_f_bytes;   // bytes reserved per staged alpha row
     int soft;
-    int stash_bytes;   // 5 arrays * THREADS * VPT * 4
+    int stash_bytes;   // 4 arrays * THREADS * VPT * 4 (mz*P, rc, c2, c3)
     __host__ __device__ int header_bytes() const { return 128 + kBwdSlots * kXStride * 4 + 128; }
-    // p ring (3) [+ energy ring (3)] + alpha ring (3) + stash
+    // p ring (3) [+ energy ring (3)] + alpha ring (3) + g'' slots (2) [+ grad_beta slot] + stash
     __host__ __device__ size_t total() const {
-        return (size_t)header_bytes() + (size_t)(soft ? 6 : 3) * row_t_bytes + (size_t)3 * row_f_bytes + (size_t)stash_bytes;
+        return (size_t)header_bytes() + (size_t)(soft ? 6 : 3) * row_t_bytes +
+               (size_t)(soft ? 6 : 5) * row_f_bytes + (size_t)stash_bytes;
     }
 };
 
@@ -54,13 +57,16 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
     static_assert(VPT % 4 == 0, "VPT must be a multiple of 4");
 
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);       // [0..2] p ring, [3..5] energy ring, [6..8] alpha ring
+    // mbarriers: [0..2] p ring, [3..5] energy ring, [6..8] alpha ring, [9] grad_beta, [10..11] grad_alpha
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     float* xb = reinterpret_cast<float*>(smem + 128);         // [kBwdSlots][32]
     float* bcast = xb + kBwdSlots * kXStride;                 // [0] 1/D at the mass-preservation column
     unsigned char* ring_p = smem + plan.header_bytes();
     unsigned char* ring_e = ring_p + 3 * plan.row_t_bytes;
     unsigned char* ring_a = ring_e + (SOFT ? 3 * plan.row_t_bytes : 0);
-    float4* stash = reinterpret_cast<float4*>(ring_a + 3 * plan.row_f_bytes);
+    unsigned char* slot_g = ring_a + 3 * plan.row_f_bytes;                       // 2 x g'' / grad_alpha (linear rows)
+    unsigned char* slot_b = slot_g + 2 * plan.row_f_bytes;                       // grad_beta row
+    float4* stash = reinterpret_cast<float4*>(slot_b + (SOFT ? plan.row_f_bytes : 0));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = blockIdx.x;
@@ -103,7 +109,7 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
     int last = S - 1;
 
     if (tid == 0) {
-        for (int b = 0; b < 9; ++b) mbar_init(&bars[b], 1);
+        for (int b = 0; b < 12; ++b) mbar_init(&bars[b], 1);
         mbar_fence_init();
     }
     if (mp_add) {
@@ -145,7 +151,20 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
         mbar_expect_tx(&bars[6 + k], f_bytes);
         tma_load_1d(const_cast<float*>(slot_a(k)), al + (size_t)r * S, f_bytes, &bars[6 + k]);
     };
+    // grad_alpha row r -> g'' slot (T-1-r) & 1 ; grad_beta row r -> the single slot
+    auto gslot = [&](int k2) { return reinterpret_cast<float*>(slot_g + (size_t)k2 * plan.row_f_bytes); };
+    auto issue_ga = [&](int r) {
+        const int k = (T_len - 1 - r) & 1;
+        mbar_expect_tx(&bars[10 + k], f_bytes);
+        tma_load_1d(gslot(k), gA_in + (size_t)r * S, f_bytes, &bars[10 + k]);
+    };
+    auto issue_gb = [&](int r) {
+        mbar_expect_tx(&bars[9], f_bytes);
+        tma_load_1d(slot_b, gB_in + (size_t)r * S, f_bytes, &bars[9]);
+    };
     if (tid == 0) {
+        if (has_ga) issue_ga(T_len - 1);
+        if (has_gb) issue_gb(T_len - 1);
         issue_p(T_len - 1);
         if (SOFT) {
             issue_e(T_len - 1);
@@ -183,16 +202,14 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
         for (int q = 0; q < Q4; ++q)
             stash[(arr * Q4 + q) * THREADS + tid] = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
     };
-    auto ldg_row = [&](const float* base, bool present, int row, float2 (&v)[H]) {
-        if (present) {
-            float t[VPT];
-            ld_row_f32<VPT>(base + (size_t)row * S, j0, S, vec, t);
+    auto lin_ld = [&](const float* row, float2 (&v)[H]) {     // linear fp32 row in shared memory
+        unsigned dummy = 0u;
+        lds_row2<float, VPT, false>(row + j0, v, dummy);
+    };
+    auto lin_st = [&](float* row, const float2 (&v)[H]) {
 #pragma unroll
-            for (int q = 0; q < H; ++q) v[q] = f2(t[2 * q], t[2 * q + 1]);
-        } else {
-#pragma unroll
-            for (int q = 0; q < H; ++q) v[q] = f2(0.f);
-        }
+        for (int q = 0; q < Q4; ++q)
+            *reinterpret_cast<float4*>(row + j0 + 4 * q) = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
     };
 
     auto body = [&](auto steady_c, const int s) __attribute__((always_inline)) {
@@ -205,6 +222,9 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
         if (km == 3) { km = 0; parm ^= 1u; }
         int kl = kp - 1;                    // ring position of row s+1
         if (kl < 0) kl = 2;
+        const int kg = (T_len - 1 - s) & 1;             // g'' / grad_alpha slot of step s
+        const unsigned parg = ((unsigned)(T_len - 1 - s) >> 1) & 1u;
+        const unsigned parb = (unsigned)(T_len - 1 - s) & 1u;
 
         // ================================================================ PRE-B1
         // ---- MAXS(s-1): row max and first arg-max of the energies
@@ -259,8 +279,8 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
         float ginc = 0.f;
         if (doL) {
             float2 gpp[H], Pm[H];
-            stash_ld(0, gpp);
-            stash_ld(1, Pm);
+            lin_ld(gslot(kg ^ 1), gpp);          // g''(s+1)
+            stash_ld(0, Pm);
 #pragma unroll
             for (int q = 0; q < H; ++q) g0[q] = add2(gpp[q], carry[q]);
             float at = 0.f;
@@ -314,9 +334,9 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
             const float gbase = xw_suffix_add<NW>(xb + 2 * kXStride, warp, lane) + gexc;
             const float2 gb2 = f2(gbase);
             float2 rcL[H], c2[H], c3[H], pL[H];
-            stash_ld(2, rcL);
-            stash_ld(3, c2);
-            stash_ld(4, c3);
+            stash_ld(1, rcL);
+            stash_ld(2, c2);
+            stash_ld(3, c3);
             unsigned dummy = 0u;
             lds_row2<T, VPT, false>(slot_p(kl) + j0, pL, dummy);
             float2 gAk[H];
@@ -338,16 +358,16 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
         // ---- EARLY(s) S1 finish: cp, 1/c, P ; 1/D ; alpha_{s-1} ; c2.  rc and c2 go to the stash in
         //      their final form, cp and P are parked there until the z mask is known (POST-B2);
         //      LATE(s+1) has just read its own copies above.
-        float2 rD[H], gB[H], sl[H], Rl[H], Wl[H];
+        float2 rD[H], sl[H], Rl[H], Wl[H];
         float uinc = 0.f, rinc = 0.f, winc = 0.f;
         if (doE) {
             const float xoff = xw_prefix_mul<NW>(xb + 0 * kXStride, warp, lane);
             const float cbase = (one_eps * xoff) * xexc;
             float2 cp[H], rc[H], P[H], am1[H];
             finish_cumprod<VPT>(cbase, cpre, p_s, eps, cp, rc, P);
-            stash_st(1, P);
-            stash_st(2, rc);
-            stash_st(4, cp);
+            stash_st(0, P);
+            stash_st(1, rc);
+            stash_st(3, cp);
             if (s > 0) {
                 mbar_wait(&bars[6 + km], parm);
                 unsigned dummy = 0u;
@@ -377,9 +397,9 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
                     const float cpk = SIMULST_EL(cp, k), rck = SIMULST_EL(rc, k);
                     const bool pass = cpk >= eps && cpk <= 1.0f;
                     const float u = SIMULST_EL(am1, k) * rck;
-                    SIMULST_EL(c2, k) = pass ? (rck * u) * cpk : 0.f;
+                    SIMULST_EL(c2, k) = pass ? u : 0.f;        // rc * u * cp with rc * cp = 1 inside the clamp
                 }
-                stash_st(3, c2);
+                stash_st(2, c2);
             }
             if (SOFT) {
                 const float ebase = xw_prefix_add<NW>(xb + 1 * kXStride, warp, lane) + eexc;
@@ -389,7 +409,6 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
                     for (int k = 0; k < VPT; ++k)
                         if (at_last(k)) bcast[0] = SIMULST_EL(rD, k);
                 }
-                ldg_row(gB_in, has_gb, s, gB);
                 // r = alpha'_s / D with alpha'_s (the row as stored) still in the ring
                 if (s == T_len - 1) mbar_wait(&bars[6 + kp], par3);
                 float2 r[H];
@@ -457,13 +476,13 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
             st_row_t<T, VPT, FULL>(gp_out + (size_t)(s + 1) * S, j0, S, vec, o8);
         }
         // ---- EARLY(s) S2 finish: s, z mask -> final mz*P and c3 in the stash ; R, W, gb, gR
-        float2 gR[H], ge1[H], W[H], gA[H], exm[H];
+        float2 gR[H], ge1[H], W[H], exm[H];
         float gA_last = 0.f;
         if (doE) {
             const float ubase = xw_prefix_add<NW>(xb + 6 * kXStride, warp, lane) + uexc;
             float2 P[H], cp[H], sfull[H], z[H];
-            stash_ld(1, P);
-            stash_ld(4, cp);
+            stash_ld(0, P);
+            stash_ld(3, cp);
             finish_u_prefix<VPT>(ubase, sl, P, sfull, z);
 #pragma unroll
             for (int k = 0; k < VPT; ++k) {
@@ -471,12 +490,20 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
                 if (!inside) SIMULST_EL(P, k) = 0.f;                             // mz * P
                 SIMULST_EL(cp, k) = inside ? SIMULST_EL(sfull, k) * SIMULST_EL(cp, k) : 0.f;   // c3 = mz * s * cp
             }
-            stash_st(1, P);
-            stash_st(4, cp);
+            stash_st(0, P);
+            stash_st(3, cp);
             if (SOFT) {
                 const float2 rb = f2(xw_suffix_add<NW>(xb + 7 * kXStride, warp, lane) + rexc);
                 const float2 wb = f2(xw_suffix_add<NW>(xb + 8 * kXStride, warp, lane) + wexc);
                 const float2 me = f2(-eps);
+                float2 gB[H];
+                if (has_gb) {
+                    mbar_wait(&bars[9], parb);
+                    lin_ld(reinterpret_cast<const float*>(slot_b), gB);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < H; ++q) gB[q] = f2(0.f);
+                }
 #pragma unroll
                 for (int q = 0; q < H; ++q) {
                     const float2 R = add2(rb, Rl[q]);
@@ -494,8 +521,12 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
                     exm[q] = add2(ex[q], me);                                    // exp(E - m) up to an ulp of e
                 }
             }
-            ldg_row(gA_in, has_ga, s, gA);
-            if (mp && has_ga) gA_last = gA_in[(size_t)s * S + last];
+            // grad_alpha row s has landed in the g'' slot: the column mass preservation reads must
+            // be fetched before the barrier, its owner overwrites it with g'' afterwards
+            if (has_ga) {
+                mbar_wait(&bars[10 + kg], parg);
+                if (mp) gA_last = gslot(kg)[last];
+            }
         }
         if (SOFT) {
             // ============================================================ PRE-B3
@@ -535,10 +566,14 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
                     okg = ok * (gA_last + gtotal * bcast[0]);
                 }
                 float gEm[VPT];
-                float2 g2[H];
+                float2 g2[H], gA[H];
+                if (has_ga) {
+                    lin_ld(gslot(kg), gA);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < H; ++q) gA[q] = f2(0.f);
+                }
                 float gsum = 0.f;
-                gEm_fix = 0.f;
-                fix_col = -1;
 #pragma unroll
                 for (int k = 0; k < VPT; ++k) {
                     const float grx = gbase + (k == 0 ? 0.f : SIMULST_EL(grl, k - (k == 0 ? 0 : 1)));   // exclusive prefix
@@ -549,14 +584,24 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
                     const bool live = is_live(k);
                     gEm[k] = live ? ge * SIMULST_EL(exm, k) : 0.f;
                     gsum += gEm[k];
-                    if (j0 + k == amax_cur) { gEm_fix = gEm[k]; fix_col = j0 + k; }
                     float g = live ? (SIMULST_EL(gA, k) + gsoft) - okg : 0.f;
                     if (mp && !mp_add && at_last(k)) g = 0.f;      // replaced column
                     SIMULST_EL(g2, k) = g;
                 }
                 gEsum_prev = gsum;
                 st_row_t<T, VPT, FULL>(ge_out + (size_t)s * S, j0, S, vec, gEm);
-                stash_st(0, g2);
+                lin_st(gslot(kg), g2);
+                fence_proxy_async();        // this slot is refilled by a bulk copy next step
+                // the thread that owns the arg-max column keeps its value for the deferred correction
+                fix_col = -1;
+                const int d = amax_cur - j0;
+                if ((unsigned)d < (unsigned)VPT) {
+                    fix_col = amax_cur;
+                    gEm_fix = gEm[0];
+#pragma unroll
+                    for (int k = 1; k < VPT; ++k)
+                        if (d == k) gEm_fix = gEm[k];
+                }
             }
         } else {
             if (doE) {
@@ -566,24 +611,39 @@ mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
                     const float ok = (row_total >= 0.0f && row_total <= 1.0f) ? 1.0f : 0.0f;
                     okg = ok * gA_last;
                 }
-                float2 g2[H];
+                float2 g2[H], gA[H];
+                if (has_ga) {
+                    lin_ld(gslot(kg), gA);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < H; ++q) gA[q] = f2(0.f);
+                }
+                __syncthreads();            // gA_last (read above by everyone) is about to be overwritten
 #pragma unroll
                 for (int k = 0; k < VPT; ++k) {
                     float g = is_live(k) ? SIMULST_EL(gA, k) - okg : 0.f;
                     if (mp && !mp_add && at_last(k)) g = 0.f;
                     SIMULST_EL(g2, k) = g;
                 }
-                stash_st(0, g2);
+                lin_st(gslot(kg), g2);
+                fence_proxy_async();        // this slot is refilled by a bulk copy next step
+            } else {
+                __syncthreads();
             }
             __syncthreads();                // ring slots below must not be refilled while still read
         }
 
         // ---- ring refills (every read of this iteration's rows is behind the last barrier):
         //      rows s (energy, alpha) and s+1 (p) are dead
+        //      rows s (energy, alpha, grad_beta) and s+1 (p, g'') are dead
         if (tid == 0) {
             if (SOFT && s - 3 >= 0) issue_e(s - 3);
             if (s - 2 >= 0) issue_p(s - 2);
             if (s - 3 >= 0) issue_a(s - 3);
+            if (s - 1 >= 0 && s - 1 < T_len) {
+                if (has_ga && s - 1 <= T_len - 2) issue_ga(s - 1);
+                if (has_gb && s <= T_len - 1) issue_gb(s - 1);
+            }
         }
         if (++kp == 3) { kp = 0; par3 ^= 1u; }
         if (SOFT && doM) { m_cur = m_nxt; amax_cur = amax_nxt; }
@@ -609,7 +669,7 @@ int launch_mma_bwd_pipe_impl(const MmaParams& prm, cudaStream_t stream) {
     plan.row_t_bytes = (CAP * (int)sizeof(T) + 127) / 128 * 128;
     plan.row_f_bytes = (CAP * 4 + 127) / 128 * 128;
     plan.soft = SOFT ? 1 : 0;
-    plan.stash_bytes = 5 * CAP * 4;
+    plan.stash_bytes = 4 * CAP * 4;
     const size_t budget = THREADS <= 128 ? 56 * 1024 : (THREADS <= 256 ? 110 * 1024 : 220 * 1024);
     if (plan.total() > budget) return 1;
     auto kern = mma_bwd_pipe_kernel<THREADS, VPT, T, SOFT, FULL>;
