@@ -75,6 +75,9 @@ int simulst_mma_set_tma(int enable);
 /* 1 = software-pipelined training kernels for hard / infinite-lookback attention when rows
  * can be TMA-staged (default), 0 = always the generic (one scan per barrier) kernels */
 int simulst_mma_set_pipeline(int enable);
+/* 1 = CIF forward/backward through the TMA-staged tile kernels when rows are 16-byte aligned
+ * and C <= 512 (default), 0 = always the per-warp kernels (same results bit for bit) */
+int simulst_cif_set_tile(int enable);
 
 /* ---------------------------------------------------------------------------------------
  * MMA training path, forward.   Replaces, fused in one launch,
@@ -205,11 +208,16 @@ int simulst_mma_step(const void* p_choose, int p_dtype,
  *   lengths        [B] int64 out   feat_lengths before tail handling
  *   t_max          [1] int32 i/o   inference: atomicMax of lengths (caller zeroes it); may be
  *                                  NULL in training
+ *   seg_first      [B,seg_stride] int32 out  segment table: seg_first[b,t] = first frame whose
+ *                                  firing index floor(csum/beta) reaches t (S if none), so that
+ *                                  output slot t draws from frames seg_first[t]..seg_first[t+1].
+ *                                  seg_stride >= T+2 (training) / floor(S/beta)+3 (inference)
  */
 int simulst_cif_plan(const void* alpha, int a_dtype, const uint8_t* padding_mask,
                      const float* desired_sum, const int64_t* target_lengths,
                      float* csum, float* scale, float* alpha_sum, int64_t* lengths,
-                     int* t_max, int B, int S, float beta, unsigned* status, void* stream);
+                     int* t_max, int32_t* seg_first, int seg_stride, int B, int S, float beta,
+                     unsigned* status, void* stream);
 
 /* Pass 2, simulst_cif_fwd: weighted segment sums, one warp per output slot (every slot reads
  * one contiguous source range; deterministic, no atomics), fused with the inference tail
@@ -217,6 +225,7 @@ int simulst_cif_plan(const void* alpha, int a_dtype, const uint8_t* padding_mask
  *   input        [B,S,C] x_dtype
  *   T            max over rows of `lengths` (firing indices are clipped to it, cif.py:82)
  *   T_alloc      slots computed per row: T in training, T+1 in inference
+ *   seg_first    [B,seg_stride] int32   the table written by simulst_cif_plan
  *   cif_out      [B,T_alloc,C] x_dtype out     delays [B,T_alloc] x_dtype out
  *   tail_weights [B] fp32 out      (inference)  lengths_out [B] int64 out (inference: lengths
  *                                  + 1 where the tail fires)   t_max2 [1] int32 i/o: atomicMax of
@@ -224,6 +233,7 @@ int simulst_cif_plan(const void* alpha, int a_dtype, const uint8_t* padding_mask
  */
 int simulst_cif_fwd(const void* input, int x_dtype, const float* csum, const float* scale,
                     const void* alpha, int a_dtype, const uint8_t* padding_mask,
+                    const int32_t* seg_first, int seg_stride,
                     void* cif_out, void* delays, float* tail_weights,
                     const int64_t* lengths, int64_t* lengths_out, int* t_max2,
                     int B, int S, int C, int T, int T_alloc,

@@ -10,6 +10,10 @@
 //          every slot strictly in between gets beta
 // left/right are non-decreasing in s, so output slot t draws from the contiguous frame range
 // [first(t), first(t+1)] with first(t) = min{s : right_s >= t}: one warp per slot streams it.
+#include <algorithm>
+#include <initializer_list>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace simulst {
@@ -28,7 +32,8 @@ __global__ void __launch_bounds__(kPlanThreads)
 cif_plan_kernel(const TA* __restrict__ alpha, const uint8_t* __restrict__ mask,
                 const float* __restrict__ desired_sum, const int64_t* __restrict__ target_lengths,
                 float* __restrict__ csum, float* __restrict__ scale_out, float* __restrict__ alpha_sum,
-                int64_t* __restrict__ lengths, int* __restrict__ t_max, int S, float beta,
+                int64_t* __restrict__ lengths, int* __restrict__ t_max,
+                int* __restrict__ seg_first, int seg_stride, int S, float beta,
                 unsigned* status) {
     extern __shared__ float sm[];
     float* a = sm;
@@ -37,6 +42,8 @@ cif_plan_kernel(const TA* __restrict__ alpha, const uint8_t* __restrict__ mask,
     const TA* a_row = alpha + (size_t)b * S;
     const uint8_t* m_row = mask ? mask + (size_t)b * S : nullptr;
     unsigned bits = 0u;
+    int* f_row = seg_first + (size_t)b * seg_stride;
+    for (int t = tid; t < seg_stride; t += kPlanThreads) f_row[t] = S;     // "no frame reaches slot t"
     // The row has only S elements, so everything here accumulates in fp64 and rounds each
     // output to fp32 once -- the rounding behaviour of torch's CPU cumsum (double accumulator),
     // which keeps the firing indices floor(csum / beta) bit-identical to the reference's except
@@ -96,6 +103,18 @@ cif_plan_kernel(const TA* __restrict__ alpha, const uint8_t* __restrict__ mask,
         alpha_sum[b] = tot;
         if (target_lengths != nullptr) lengths[b] = target_lengths[b];
     }
+    // segment table: seg_first[t] = first frame whose (unclipped) firing index reaches t.  Firing
+    // indices are re-derived from the STORED fp32 csum so every kernel sees the same integers.
+    __syncthreads();
+    {
+        const float lim = (float)(seg_stride - 1);
+        for (int j = lo; j < hi; ++j) {
+            const float qf = fminf(floorf(__fdiv_rn(c_row[j], beta)), lim);
+            const float pf = (j == 0) ? -1.0f : fminf(floorf(__fdiv_rn(c_row[j - 1], beta)), lim);
+            const int q = (int)qf;
+            for (int t = (int)pf + 1; t <= q; ++t) f_row[t] = j;
+        }
+    }
     if (target_lengths == nullptr && hi == S && lo < S) {
         // cif.py:75, evaluated on the scan's own last element so that the row length and the
         // firing indices can never disagree
@@ -104,27 +123,6 @@ cif_plan_kernel(const TA* __restrict__ alpha, const uint8_t* __restrict__ mask,
         atomicMax(t_max, (int)len);
     }
     flag_status(status, bits);
-}
-
-// ---------------------------------------------------------------------------- k-ary search
-// smallest s in [0, S) with cs[s] / beta >= t (cs non-decreasing); S if none.  Warp-cooperative.
-__device__ __forceinline__ int first_frame(const float* __restrict__ cs, int S, float beta, float t, int lane) {
-    int lo = 0, hi = S;
-    while (hi - lo > kWarp) {
-        const int step = (hi - lo + kWarp - 1) / kWarp;
-        const int pos = min(lo + (lane + 1) * step - 1, hi - 1);
-        const bool ok = __fdiv_rn(cs[pos], beta) >= t;
-        const unsigned m = __ballot_sync(kFull, ok);
-        if (m == 0u) return hi == S ? S : hi;       // cannot happen for hi < S (invariant), kept for safety
-        const int f = __ffs(m) - 1;
-        const int nlo = lo + f * step;
-        hi = min(lo + (f + 1) * step, hi);
-        lo = nlo;
-    }
-    const int pos = lo + lane;
-    const bool ok = pos < hi && __fdiv_rn(cs[pos], beta) >= t;
-    const unsigned m = __ballot_sync(kFull, ok);
-    return m ? lo + __ffs(m) - 1 : hi;
 }
 
 // weight of frame s for output slot t (l = left, r = right, both already clipped to T)
@@ -136,17 +134,31 @@ __device__ __forceinline__ float slot_weight(int t, int l, int r, float a, float
     return beta;
 }
 
-// ---------------------------------------------------------------------------- forward
-constexpr int kFwdWarps = 4;
+}  // namespace simulst
 
-template <typename TX, typename TA>
+#include "cif_tile.cuh"
+
+namespace simulst {
+
+// ---------------------------------------------------------------------------- forward (fallback)
+constexpr int kFwdWarps = 4;
+constexpr int kCifV = 4;            // channels per lane per pack
+constexpr int kFwdUnroll = 4;       // frames whose loads are in flight together
+
+// One warp per output slot (b, t).  The slot's frame range [seg_first[t], seg_first[t+1]] comes
+// from the plan kernel's table; lanes first evaluate the per-frame weights of up to 32 frames
+// in parallel, then the warp streams the frames (lanes over channels, NP packs of 4 channels per
+// lane, kFwdUnroll frames of loads in flight).  Accumulation order is frame order: deterministic.
+template <typename TX, typename TA, int NP>
 __global__ void __launch_bounds__(kFwdWarps * kWarp)
 cif_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ csum, const float* __restrict__ scale,
                const TA* __restrict__ alpha, const uint8_t* __restrict__ mask,
+               const int* __restrict__ seg_first, int seg_stride,
                TX* __restrict__ out, TX* __restrict__ delays, float* __restrict__ tail_weights,
                const int64_t* __restrict__ lengths, int64_t* __restrict__ lengths_out,
                int* __restrict__ t_max2,
                int B, int S, int C, int T, int T_alloc, float beta, float tail_thres, int training) {
+    constexpr int V = kCifV;
     const int lane = threadIdx.x & 31;
     const long long slot = (long long)blockIdx.x * kFwdWarps + (threadIdx.x >> 5);
     if (slot >= (long long)B * T_alloc) return;
@@ -157,43 +169,65 @@ cif_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ csum, const f
     const float sc = scale[b];
     const TX* xb = x + (size_t)b * S * C;
     TX* o_row = out + ((size_t)b * T_alloc + t) * C;
+    const int* f_row = seg_first + (size_t)b * seg_stride;
 
-    const int s_lo = first_frame(cs, S, beta, (float)t, lane);
-    int s_hi = (t >= T) ? S - 1 : min(first_frame(cs, S, beta, (float)(t + 1), lane), S - 1);
-
-    constexpr int V = 4;
+    const int s_lo = (t < seg_stride) ? f_row[t] : S;
+    const int s_hi = (t >= T || t + 1 >= seg_stride) ? S - 1 : min(f_row[t + 1], S - 1);
     const bool vec = (C % V == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) % (V * sizeof(TX)) == 0);
+
     float wsum = 0.f, dsum = 0.f;
-    // accumulate up to 4 packs of V channels per lane per pass over the frame range
-    for (int c0 = 0; c0 < C; c0 += kWarp * V * 4) {
-        float acc[4][V];
+    for (int c0 = 0; c0 < max(C, 1); c0 += kWarp * V * NP) {       // (C == 0 still yields delays)
+        float acc[NP][V];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < NP; ++q)
 #pragma unroll
             for (int k = 0; k < V; ++k) acc[q][k] = 0.f;
         float ws = 0.f, ds = 0.f;
-        int l = (s_lo <= 0) ? 0 : fire_index(cs[s_lo - 1], beta, T);
-        for (int s = s_lo; s <= s_hi; ++s) {
-            const float c_s = cs[s];
-            const int r = fire_index(c_s, beta, T);
-            const float a = (m_row && m_row[s]) ? 0.f : to_f32<TA>(a_row[s]) * sc;
-            if (t >= l && t <= r) {
-                const float w = slot_weight(t, l, r, a, c_s, beta);
-                ws += w;
-                ds += (l != r && t != l && t != r) ? (float)(s + 1) : __fdiv_rn(w * (float)(s + 1), beta);
-                const TX* xs = xb + (size_t)s * C;
+        for (int base = s_lo; base <= s_hi; base += kWarp) {
+            // ---- per-frame weight of this slot, one frame per lane
+            const int s = base + lane;
+            float w = 0.f, d = 0.f;
+            if (s <= s_hi) {
+                const float c_s = cs[s];
+                const int r = fire_index(c_s, beta, T);
+                const int l = (s == 0) ? 0 : fire_index(cs[s - 1], beta, T);
+                const float a = (m_row && m_row[s]) ? 0.f : to_f32<TA>(a_row[s]) * sc;
+                if (t >= l && t <= r) {
+                    w = slot_weight(t, l, r, a, c_s, beta);
+                    d = (l != r && t != l && t != r) ? (float)(s + 1) : __fdiv_rn(w * (float)(s + 1), beta);
+                }
+            }
+            const int n = min(kWarp, s_hi - base + 1);
+            for (int f0 = 0; f0 < n; f0 += kFwdUnroll) {
+                float xv[kFwdUnroll][NP][V];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int c = c0 + (q * kWarp + lane) * V;
-                    if (c < C) {
-                        float xv[V];
-                        load_vec<TX, V>(xs + c, C - c, vec, 0.f, xv);
+                for (int u = 0; u < kFwdUnroll; ++u) {
+                    const TX* xs = xb + (size_t)(base + f0 + u) * C;
 #pragma unroll
-                        for (int k = 0; k < V; ++k) acc[q][k] += w * xv[k];
+                    for (int q = 0; q < NP; ++q) {
+                        const int c = c0 + (q * kWarp + lane) * V;
+                        if (f0 + u < n && c < C) {
+                            load_vec<TX, V>(xs + c, C - c, vec, 0.f, xv[u][q]);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < V; ++k) xv[u][q][k] = 0.f;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kFwdUnroll; ++u) {
+                    const float wu = __shfl_sync(kFull, w, (f0 + u) & 31);
+                    const float du = __shfl_sync(kFull, d, (f0 + u) & 31);
+                    if (f0 + u < n) {
+                        ws += wu;
+                        ds += du;
+#pragma unroll
+                        for (int q = 0; q < NP; ++q)
+#pragma unroll
+                            for (int k = 0; k < V; ++k) acc[q][k] += wu * xv[u][q][k];
                     }
                 }
             }
-            l = r;
         }
         if (c0 == 0) { wsum = ws; dsum = ds; }
         // tail handling (inference): the slot at the row's own length holds the partial segment
@@ -208,7 +242,7 @@ cif_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ csum, const f
             }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < NP; ++q) {
             const int c = c0 + (q * kWarp + lane) * V;
             if (c < C) {
                 float ov[V];
@@ -218,7 +252,6 @@ cif_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ csum, const f
             }
         }
     }
-    if (C == 0) return;
     if (lane == 0) {
         delays[(size_t)b * T_alloc + t] = from_f32<TX>(dsum);
         if (!training && t == lengths[b]) {
@@ -232,7 +265,11 @@ cif_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ csum, const f
 }
 
 // ---------------------------------------------------------------------------- backward, per frame
-template <typename TX, typename TA>
+// One warp per source frame: grad_input[s] = sum over the slots l..r the frame feeds of
+// weight * grad_out[slot], and the two weight gradients <grad_out[l], x_s>, <grad_out[r], x_s>.
+// The x row and the grad_out rows of slots l and r (the only ones unless a frame fires more
+// than once) are requested together before any of them is consumed.
+template <typename TX, typename TA, int NP>
 __global__ void __launch_bounds__(kFwdWarps * kWarp)
 cif_bwd_frame_kernel(const TX* __restrict__ x, const float* __restrict__ csum, const float* __restrict__ scale,
                      const TA* __restrict__ alpha, const uint8_t* __restrict__ mask,
@@ -241,18 +278,25 @@ cif_bwd_frame_kernel(const TX* __restrict__ x, const float* __restrict__ csum, c
                      const int64_t* __restrict__ len1,
                      TX* __restrict__ g_x, float* __restrict__ ws_gl, float* __restrict__ ws_gd,
                      int B, int S, int C, int T, int T_out, float beta, float tail_thres, int training) {
+    constexpr int V = kCifV;
     const int lane = threadIdx.x & 31;
     const long long fr = (long long)blockIdx.x * kFwdWarps + (threadIdx.x >> 5);
     if (fr >= (long long)B * S) return;
     const int b = (int)(fr / S), s = (int)(fr % S);
     const float* cs = csum + (size_t)b * S;
-    const float c_s = cs[s];
-    const int r = fire_index(c_s, beta, T);
-    const int l = (s == 0) ? 0 : fire_index(cs[s - 1], beta, T);
-    const bool pad = mask && mask[(size_t)b * S + s];
-    const float a = pad ? 0.f : to_f32<TA>(alpha[(size_t)b * S + s]) * scale[b];
     const TX* xs = x + ((size_t)b * S + s) * C;
     TX* gx = g_x + ((size_t)b * S + s) * C;
+    const bool vec = (C % V == 0) &&
+                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g_out) |
+                       reinterpret_cast<uintptr_t>(g_x)) % (V * sizeof(TX)) == 0);
+    const float c_s = cs[s];
+    const float c_p = (s == 0) ? 0.f : cs[s - 1];
+    const bool pad = mask && mask[(size_t)b * S + s];
+    const float a_raw = to_f32<TA>(alpha[(size_t)b * S + s]);
+    const float sc = scale[b];
+    const int r = fire_index(c_s, beta, T);
+    const int l = (s == 0) ? 0 : fire_index(c_p, beta, T);
+    const float a = pad ? 0.f : a_raw * sc;
     const float pos = (float)(s + 1);
 
     // output rows that exist and were not zeroed; the tail row carries the detached upscale
@@ -262,39 +306,64 @@ cif_bwd_frame_kernel(const TX* __restrict__ x, const float* __restrict__ csum, c
         l0 = len0[b]; l1 = len1[b];
         if (l1 > l0) tail_mul = __fdiv_rn(beta, tail_weights[b]);
     }
-    constexpr int V = 4;
-    const bool vec = (C % V == 0) &&
-                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g_out) |
-                       reinterpret_cast<uintptr_t>(g_x)) % (V * sizeof(TX)) == 0);
+    // a slot contributes iff it was kept (t < T_out) and, in inference, not zeroed (t < l1)
+    auto live = [&](int t) -> bool { return t < T_out && (training || t < l1); };
+    auto factor = [&](int t) -> float { return (!training && t == l0 && l1 > l0) ? tail_mul : 1.0f; };
+
     float dot_l = 0.f, dot_r = 0.f;
-    for (int c0 = 0; c0 < C; c0 += kWarp * V) {
-        const int c = c0 + lane * V;
-        float xv[V], acc[V];
+    for (int c0 = 0; c0 < C; c0 += kWarp * V * NP) {
+        float xv[NP][V], acc[NP][V], gl[NP][V], gr[NP][V];
+        const bool use_l = live(l), use_r = r > l && live(r);
+        const TX* gl_row = g_out + ((size_t)b * T_out + l) * C;
+        const TX* gr_row = g_out + ((size_t)b * T_out + r) * C;
 #pragma unroll
-        for (int k = 0; k < V; ++k) { xv[k] = 0.f; acc[k] = 0.f; }
-        if (c < C) load_vec<TX, V>(xs + c, C - c, vec, 0.f, xv);
-        for (int t = l; t <= r; ++t) {
-            if (t >= T_out) break;                          // sliced-off dump slot(s)
-            float f = 1.0f;
-            if (!training) {
-                if (t >= l1) continue;                      // zeroed tail rows: no gradient
-                if (t == l0 && l1 > l0) f = tail_mul;
-            }
-            const float w = slot_weight(t, l, r, a, c_s, beta);
+        for (int q = 0; q < NP; ++q) {
+            const int c = c0 + (q * kWarp + lane) * V;
+#pragma unroll
+            for (int k = 0; k < V; ++k) { xv[q][k] = 0.f; acc[q][k] = 0.f; gl[q][k] = 0.f; gr[q][k] = 0.f; }
             if (c < C) {
-                float gv[V];
-                load_vec<TX, V>(g_out + ((size_t)b * T_out + t) * C + c, C - c, vec, 0.f, gv);
-                float d = 0.f;
-#pragma unroll
-                for (int k = 0; k < V; ++k) {
-                    acc[k] += (w * f) * gv[k];
-                    d += gv[k] * xv[k];
-                }
-                if (t == l) dot_l += d * f;
-                if (t == r) dot_r += d * f;
+                load_vec<TX, V>(xs + c, C - c, vec, 0.f, xv[q]);
+                if (use_l) load_vec<TX, V>(gl_row + c, C - c, vec, 0.f, gl[q]);
+                if (use_r) load_vec<TX, V>(gr_row + c, C - c, vec, 0.f, gr[q]);
             }
         }
-        if (c < C) store_vec<TX, V>(gx + c, C - c, vec, acc);
+        // slot t with its grad_out pack gv: acc += (w f) gv ; d = <gv, x>
+        auto apply = [&](int t, const float (&gv)[NP][V]) {
+            const float f = factor(t);
+            const float w = slot_weight(t, l, r, a, c_s, beta);
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                if (c0 + (q * kWarp + lane) * V < C) {
+                    float d = 0.f;
+#pragma unroll
+                    for (int k = 0; k < V; ++k) {
+                        acc[q][k] += (w * f) * gv[q][k];
+                        d += gv[q][k] * xv[q][k];
+                    }
+                    if (t == l) dot_l += d * f;
+                    if (t == r) dot_r += d * f;
+                }
+            }
+        };
+        if (use_l) apply(l, gl);
+        for (int t = l + 1; t < r; ++t) {                   // frames that fire more than once
+            if (!live(t)) { if (t >= T_out) break; continue; }
+            float gm[NP][V];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const int c = c0 + (q * kWarp + lane) * V;
+#pragma unroll
+                for (int k = 0; k < V; ++k) gm[q][k] = 0.f;
+                if (c < C) load_vec<TX, V>(g_out + ((size_t)b * T_out + t) * C + c, C - c, vec, 0.f, gm[q]);
+            }
+            apply(t, gm);
+        }
+        if (use_r) apply(r, gr);
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const int c = c0 + (q * kWarp + lane) * V;
+            if (c < C) store_vec<TX, V>(gx + c, C - c, vec, acc[q]);
+        }
     }
     dot_l = warp_sum(dot_l);
     dot_r = warp_sum(dot_r);
@@ -372,16 +441,54 @@ static int dispatch_t(int dtype, F&& f) {
     return SIMULST_E_ARG;
 }
 
+// packs of 4 channels per lane needed to cover C channels in one pass (at most 4: 512 channels)
+template <typename F>
+static int dispatch_np(int C, F&& f) {
+    if (C <= kWarp * kCifV) return f(std::integral_constant<int, 1>{});
+    if (C <= 2 * kWarp * kCifV) return f(std::integral_constant<int, 2>{});
+    return f(std::integral_constant<int, 4>{});
+}
+
+// The tile kernels need every row (C elements) to be a whole number of 16-byte units and the
+// tensors to start on a 16-byte boundary (bulk-copy alignment), and C <= 512 (one pass).
+static bool tile_ok(int C, size_t esize, std::initializer_list<const void*> ptrs) {
+    if (C <= 0 || C > 4 * kWarp * 4 || ((size_t)C * esize) % 16 != 0) return false;
+    for (const void* p : ptrs)
+        if (p != nullptr && reinterpret_cast<uintptr_t>(p) % 16 != 0) return false;
+    return true;
+}
+
+template <typename K>
+static int set_smem(K kern, size_t bytes) {
+    if (bytes > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return SIMULST_E_LAUNCH;
+    }
+    return SIMULST_OK;
+}
+
 }  // namespace simulst
 
 using namespace simulst;
 
+// development / test switch: route simulst_cif_fwd/_bwd through the per-warp fallback kernels
+static int g_cif_force_fallback = 0;
+
 extern "C" {
+
+int simulst_cif_set_tile(int enable) {
+    g_cif_force_fallback = enable ? 0 : 1;
+    return SIMULST_OK;
+}
 
 int simulst_cif_plan(const void* alpha, int a_dtype, const uint8_t* padding_mask, const float* desired_sum,
                      const int64_t* target_lengths, float* csum, float* scale, float* alpha_sum,
-                     int64_t* lengths, int* t_max, int B, int S, float beta, unsigned* status, void* stream) {
-    if (!alpha || !csum || !scale || !alpha_sum || !lengths || !valid_dtype(a_dtype)) return SIMULST_E_ARG;
+                     int64_t* lengths, int* t_max, int32_t* seg_first, int seg_stride, int B, int S, float beta,
+                     unsigned* status, void* stream) {
+    if (!alpha || !csum || !scale || !alpha_sum || !lengths || !seg_first || !valid_dtype(a_dtype))
+        return SIMULST_E_ARG;
+    if (seg_stride < 2) return SIMULST_E_SHAPE;
     if ((desired_sum == nullptr) != (target_lengths == nullptr)) return SIMULST_E_ARG;
     if (target_lengths == nullptr && t_max == nullptr) return SIMULST_E_ARG;
     if (!(beta > 0.f)) return SIMULST_E_ARG;
@@ -398,31 +505,51 @@ int simulst_cif_plan(const void* alpha, int a_dtype, const uint8_t* padding_mask
         }
         kern<<<B, kPlanThreads, smem, (cudaStream_t)stream>>>((const TA*)alpha, padding_mask, desired_sum,
                                                            target_lengths, csum, scale, alpha_sum, lengths,
-                                                           t_max, S, beta, status);
+                                                           t_max, seg_first, seg_stride, S, beta, status);
         return check_launch();
     });
 }
 
 int simulst_cif_fwd(const void* input, int x_dtype, const float* csum, const float* scale, const void* alpha,
-                    int a_dtype, const uint8_t* padding_mask, void* cif_out, void* delays,
+                    int a_dtype, const uint8_t* padding_mask, const int32_t* seg_first, int seg_stride,
+                    void* cif_out, void* delays,
                     float* tail_weights, const int64_t* lengths, int64_t* lengths_out, int* t_max2,
                     int B, int S, int C, int T, int T_alloc, float beta, float tail_thres, int training,
                     void* stream) {
-    if (!input || !csum || !scale || !alpha || !cif_out || !delays || !lengths) return SIMULST_E_ARG;
+    if (!input || !csum || !scale || !alpha || !cif_out || !delays || !lengths || !seg_first) return SIMULST_E_ARG;
+    if (seg_stride < 2) return SIMULST_E_SHAPE;
     if (!valid_dtype(x_dtype) || !valid_dtype(a_dtype)) return SIMULST_E_ARG;
     if (!training && (!tail_weights || !t_max2 || !lengths_out)) return SIMULST_E_ARG;
     if (B < 0 || S < 0 || C < 0 || T < 0 || T_alloc < 0) return SIMULST_E_SHAPE;
     if (B == 0 || T_alloc == 0 || S == 0) return SIMULST_OK;
     const long long slots = (long long)B * T_alloc;
     const unsigned blocks = (unsigned)((slots + kFwdWarps - 1) / kFwdWarps);
+    const bool tile = tile_ok(C, dtype_size(x_dtype), {input, cif_out}) && !g_cif_force_fallback;
     return dispatch_t(x_dtype, [&](auto tx) {
         using TX = decltype(tx);
         return dispatch_t(a_dtype, [&](auto ta) {
             using TA = decltype(ta);
-            cif_fwd_kernel<TX, TA><<<blocks, kFwdWarps * kWarp, 0, (cudaStream_t)stream>>>(
-                (const TX*)input, csum, scale, (const TA*)alpha, padding_mask, (TX*)cif_out, (TX*)delays,
-                tail_weights, lengths, lengths_out, t_max2, B, S, C, T, T_alloc, beta, tail_thres, training);
-            return check_launch();
+            return dispatch_np(C, [&](auto np) {
+                constexpr int NP = decltype(np)::value;
+                if (tile) {
+                    const size_t row_bytes = (size_t)C * sizeof(TX);
+                    const int FC = (int)std::max<size_t>(8, 48 * 1024 / row_bytes);
+                    const size_t smem = kTileHeader + (size_t)FC * row_bytes;
+                    auto kern = cif_fwd_tile_kernel<TX, TA, NP>;
+                    if (int rc = set_smem(kern, smem)) return rc;
+                    const unsigned grid = (unsigned)((long long)B * ((T_alloc + kTileWarps - 1) / kTileWarps));
+                    kern<<<grid, kTileThreads, smem, (cudaStream_t)stream>>>(
+                        (const TX*)input, csum, scale, (const TA*)alpha, padding_mask, seg_first, seg_stride,
+                        (TX*)cif_out, (TX*)delays, tail_weights, lengths, lengths_out, t_max2, B, S, C, T,
+                        T_alloc, beta, tail_thres, training, FC);
+                    return check_launch();
+                }
+                cif_fwd_kernel<TX, TA, NP><<<blocks, kFwdWarps * kWarp, 0, (cudaStream_t)stream>>>(
+                    (const TX*)input, csum, scale, (const TA*)alpha, padding_mask, seg_first, seg_stride,
+                    (TX*)cif_out, (TX*)delays, tail_weights, lengths, lengths_out, t_max2, B, S, C, T,
+                    T_alloc, beta, tail_thres, training);
+                return check_launch();
+            });
         });
     });
 }
@@ -445,15 +572,34 @@ int simulst_cif_bwd(const void* input, int x_dtype, const float* csum, const flo
     const long long frames = (long long)B * S;
     const unsigned blocks = (unsigned)((frames + kFwdWarps - 1) / kFwdWarps);
     cudaStream_t st = (cudaStream_t)stream;
+    const bool tile = tile_ok(C, dtype_size(x_dtype), {input, grad_out, grad_input}) && !g_cif_force_fallback;
     int rc = dispatch_t(x_dtype, [&](auto tx) {
         using TX = decltype(tx);
         return dispatch_t(a_dtype, [&](auto ta) {
             using TA = decltype(ta);
-            cif_bwd_frame_kernel<TX, TA><<<blocks, kFwdWarps * kWarp, 0, st>>>(
-                (const TX*)input, csum, scale, (const TA*)alpha, padding_mask, (const TX*)grad_out,
-                (const TX*)grad_delays, tail_weights, lengths_before_tail, lengths_after_tail,
-                (TX*)grad_input, ws_gl, ws_gd, B, S, C, T, T_out, beta, tail_thres, training);
-            return check_launch();
+            return dispatch_np(C, [&](auto np) {
+                constexpr int NP = decltype(np)::value;
+                if (tile) {
+                    const size_t row_bytes = (size_t)C * sizeof(TX);
+                    int FR = (int)(32 * 1024 / row_bytes) / kTileWarps * kTileWarps;
+                    FR = std::max(kTileWarps, std::min(64, FR));
+                    const int GR = FR / 2 + 2;
+                    const size_t smem = kTileHeader + (size_t)(FR + GR) * row_bytes;
+                    auto kern = cif_bwd_tile_kernel<TX, TA, NP>;
+                    if (int rc2 = set_smem(kern, smem)) return rc2;
+                    const unsigned grid = (unsigned)((long long)B * ((S + FR - 1) / FR));
+                    kern<<<grid, kTileThreads, smem, st>>>(
+                        (const TX*)input, csum, scale, (const TA*)alpha, padding_mask, (const TX*)grad_out,
+                        (const TX*)grad_delays, tail_weights, lengths_before_tail, lengths_after_tail,
+                        (TX*)grad_input, ws_gl, ws_gd, B, S, C, T, T_out, beta, tail_thres, training, FR, GR);
+                    return check_launch();
+                }
+                cif_bwd_frame_kernel<TX, TA, NP><<<blocks, kFwdWarps * kWarp, 0, st>>>(
+                    (const TX*)input, csum, scale, (const TA*)alpha, padding_mask, (const TX*)grad_out,
+                    (const TX*)grad_delays, tail_weights, lengths_before_tail, lengths_after_tail,
+                    (TX*)grad_input, ws_gl, ws_gd, B, S, C, T, T_out, beta, tail_thres, training);
+                return check_launch();
+            });
         });
     });
     if (rc != SIMULST_OK) return rc;

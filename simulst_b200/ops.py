@@ -326,12 +326,16 @@ class CIFFunction(torch.autograd.Function):
             # cif.py:68 -- evaluated in the INPUT dtype, as the reference does
             desired = (beta * target_lengths.type_as(x) + eps).float().contiguous()
             t_cap = int(tl.max()) if b > 0 else 0                      # host read, cif.py:72
+        # segment table rows: slots 0..T+1 (training) / up to floor(S/beta)+1 fires (inference)
+        seg_stride = (t_cap + 2) if training else (int(s / beta) + 3)
+        seg_first = torch.empty((b, seg_stride), dtype=torch.int32, device=dev)
         st = _lib.stream_ptr(dev)
         with torch.cuda.device(dev):
             rc = lib.simulst_cif_plan(_lib.ptr(a), _lib.dtype_enum(a.dtype), _lib.ptr(mask),
                                       _lib.ptr(desired), _lib.ptr(tl), _lib.ptr(csum), _lib.ptr(scale),
                                       _lib.ptr(alpha_sum), _lib.ptr(lengths0),
-                                      counters.data_ptr(), b, s, float(beta), _lib.ptr(status), st)
+                                      counters.data_ptr(), _lib.ptr(seg_first), seg_stride,
+                                      b, s, float(beta), _lib.ptr(status), st)
             _lib.check(rc, "simulst_cif_plan")
             if not training:
                 t_cap = int(counters[0].item()) if b > 0 else 0        # host read, cif.py:76
@@ -344,6 +348,7 @@ class CIFFunction(torch.autograd.Function):
                 lengths1 = torch.empty(b, dtype=torch.int64, device=dev)
             rc = lib.simulst_cif_fwd(_lib.ptr(x), _lib.dtype_enum(x.dtype), _lib.ptr(csum), _lib.ptr(scale),
                                      _lib.ptr(a), _lib.dtype_enum(a.dtype), _lib.ptr(mask),
+                                     _lib.ptr(seg_first), seg_stride,
                                      _lib.ptr(out), _lib.ptr(delays), _lib.ptr(tail_w),
                                      _lib.ptr(lengths0), _lib.ptr(lengths1),
                                      counters.data_ptr() + 4, b, s, c, t_cap, t_alloc,

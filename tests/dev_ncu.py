@@ -15,6 +15,8 @@ ga = torch.randn(N, T, S, device=dev) * 0.01; gb = torch.randn(N, T, S, device=d
 gp = torch.empty_like(p); ge = torch.empty_like(e)
 status = torch.zeros(1, dtype=torch.int32, device=dev)
 st = torch.cuda.current_stream().cuda_stream
+import os
+lib.simulst_mma_set_pipeline(int(os.environ.get("PIPE", "1")))
 for _ in range(2):
     lib.simulst_mma_train_fwd(p.data_ptr(), 1, e.data_ptr(), 1, None, alpha.data_ptr(), beta.data_ptr(),
                               side.data_ptr(), N, T, S, 1e-6, 0, 3, status.data_ptr(), st)

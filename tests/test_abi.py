@@ -38,7 +38,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert lib.simulst_mma_set_config(0, 0) == 0
     # null pointers / bad dtype are rejected before any CUDA call
     assert lib.simulst_mma_train_fwd(None, 0, None, 0, None, None, None, None, 1, 1, 1, 1e-6, 0, 0, None, None) == -1
-    assert lib.simulst_cif_plan(None, 0, None, None, None, None, None, None, None, None, 1, 1, 1.0, None, None) == -1
+    assert lib.simulst_cif_plan(None, 0, None, None, None, None, None, None, None, None, None, 2, 1, 1, 1.0, None, None) == -1
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

@@ -181,3 +181,38 @@ def test_cif_bf16_input_close_to_fp32_oracle():
     ref = ocif.cif_function(x.bfloat16().float(), a, 1.0, 0.5, mask, tl)
     assert res["cif_out"][0].dtype == torch.bfloat16
     torch.testing.assert_close(res["cif_out"][0].float().cpu(), ref["cif_out"][0], rtol=2 ** -7, atol=2 ** -7)
+
+
+@pytest.mark.parametrize("b,s,c,beta,train,dtype", [
+    (8, 1500, 256, 1.0, True, torch.float32),
+    (8, 1500, 256, 1.0, False, torch.float32),
+    (4, 700, 80, 0.35, False, torch.float32),      # multi-fire: slots beyond the staged grad_out rows
+    (4, 700, 80, 0.35, True, torch.bfloat16),
+    (3, 2000, 512, 1.0, True, torch.float32),      # widest single-pass row
+    (5, 900, 24, 0.2, False, torch.float32),       # every frame fires several times, tiny rows
+    (2, 300, 8, 1.0, True, torch.bfloat16),        # 16-byte rows
+])
+def test_cif_tile_kernels_equal_per_warp_kernels(b, s, c, beta, train, dtype):
+    """The TMA-staged tile kernels (cif_tile.cuh) and the per-warp fallback kernels evaluate the
+    same sums in the same order: outputs and gradients must agree bit for bit."""
+    from simulst_b200 import _lib
+    lib = _lib.load()
+    x, a, mask, g = _seeded(b, s, c, seed=31 + s + c)
+    tl = None
+    if train:
+        tl = (a.masked_fill(mask, 0).sum(1) / beta).round().clamp(min=1).long()
+    outs = []
+    try:
+        for tile in (1, 0):
+            lib.simulst_cif_set_tile(tile)
+            gen = torch.Generator().manual_seed(7)
+            res, _ = _run(x, a, beta, beta / 2, mask, tl, dtype=dtype)
+            g_out = torch.randn(res["cif_out"][0].shape, generator=gen)
+            g_delay = torch.randn(res["delays"][0].shape, generator=gen)
+            res, grads = _run(x, a, beta, beta / 2, mask, tl, g_out, g_delay, dtype=dtype)
+            outs.append((res["cif_out"][0].detach().float().cpu(), res["delays"][0].detach().float().cpu(),
+                         res["cif_lengths"][0].cpu(), grads[0], grads[1]))
+    finally:
+        lib.simulst_cif_set_tile(1)
+    for got, want, what in zip(outs[0], outs[1], ("cif_out", "delays", "lengths", "grad_input", "grad_alpha")):
+        assert torch.equal(got, want), what
