@@ -81,7 +81,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-i", str(self.index), "-lms", "100"],
+                 "-i", str(self.index), "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -267,7 +267,6 @@ def run_ours(args):
     t_end.record(stream)
     barrier()
     launches = simulst_b200.launch_count()
-    clocks = sampler.stop() if rank == 0 else None
     ms_total = t_begin.elapsed_time(t_end)
     t_max = torch.tensor([ms_total], device=dev)
     if world > 1:
@@ -279,14 +278,14 @@ def run_ours(args):
     elems = N_ROWS * T * S
     value = elems * world / (ms_step * 1e-3)
 
-    # ---------------- end to end through the C ABI with HOST buffers (copies inside the region)
+    # ---------------- end to end through the public host-buffer API (copies inside the region):
+    # simulst_b200.host_pipeline.MMAHostPipeline streams row chunks H2D -> fwd+bwd -> D2H
+    from simulst_b200.host_pipeline import MMAHostPipeline
+    pipe = MMAHostPipeline(N_ROWS, T, S, dtype=dt, device=dev, chunks=args.e2e_chunks,
+                           compute_streams=args.e2e_streams, eps=EPS, mass_preservation=True, soft=True)
+
     def e2e_step():
-        p.copy_(p_host, non_blocking=True)
-        e.copy_(e_host, non_blocking=True)
-        fwd()
-        bwd()
-        gp_host.copy_(gp, non_blocking=True)
-        ge_host.copy_(ge, non_blocking=True)
+        pipe.step(p_host, e_host, ga, gb, gp_host, ge_host)
         if world > 1:
             if pending[0] is not None:
                 pending[0].wait()
@@ -296,6 +295,7 @@ def run_ours(args):
     for _ in range(2):
         e2e_step()
     barrier()
+    simulst_b200.reset_launch_count()
     t_begin.record(stream)
     for _ in range(e2e_steps):
         e2e_step()
@@ -304,12 +304,15 @@ def run_ours(args):
         pending[0] = None
     t_end.record(stream)
     barrier()
+    e2e_launches = simulst_b200.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
     e_max = torch.tensor([t_begin.elapsed_time(t_end)], device=dev)
     if world > 1:
         dist.all_reduce(e_max, op=dist.ReduceOp.MAX)
     e2e_ms = float(e_max.item()) / e2e_steps
-    h2d = p_host.numel() * 2 + e_host.numel() * 2
-    d2h = gp_host.numel() * 2 + ge_host.numel() * 2
+    h2d = pipe.h2d_bytes_per_step
+    d2h = pipe.d2h_bytes_per_step
+    simulst_b200.check_status(dev)
 
     extras = {}
     cpu_base = None
@@ -328,19 +331,21 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config(world),
-            "roofline": {"bound": "hbm", "kernel": "mma_bwd_kernel", "achieved": ach, "peak": peak,
-                         "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic("mma_bwd_kernel"),
+            "roofline": {"bound": "hbm", "kernel": "mma_bwd_pipe_kernel", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic("mma_bwd_pipe_kernel"),
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": elems * BYTES_BWD,
                          "kernel_ms": bwd_ms,
-                         "fwd": {"kernel": "mma_fwd_kernel", "kernel_ms": fwd_ms,
+                         "fwd": {"kernel": "mma_fwd_pipe_kernel", "kernel_ms": fwd_ms,
                                  "achieved": elems * BYTES_FWD / (fwd_ms * 1e-3) / 1e9,
                                  "frac": elems * BYTES_FWD / (fwd_ms * 1e-3) / 1e9 / peak,
-                                 "traffic": ncu_traffic("mma_fwd_kernel")},
+                                 "traffic": ncu_traffic("mma_fwd_pipe_kernel")},
                          "fwd_bwd_frac": elems * (BYTES_FWD + BYTES_BWD) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak},
             "e2e": {"value": elems * world / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "api": "simulst_b200.host_pipeline.MMAHostPipeline.step",
+                    "row_chunks": len(pipe.bounds), "compute_streams": len(pipe.s_comp),
+                    "gpu_launches": int(e2e_launches)},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -430,6 +435,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="row chunks of the host-buffer pipeline")
+    ap.add_argument("--e2e-streams", type=int, default=2, help="compute streams of the host-buffer pipeline")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
