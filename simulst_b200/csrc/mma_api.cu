@@ -6,7 +6,7 @@ namespace simulst {
 
 static int g_cfg_threads = 0, g_cfg_vpt = 0;   // 0 = automatic
 static int g_use_tma = 1;
-static int g_use_pipe = 1;
+static int g_use_pipe = 1;   // bit 0: pipelined forward, bit 1: pipelined backward
 
 struct Config { int threads, vpt; };
 
@@ -70,8 +70,9 @@ int simulst_mma_set_tma(int enable) {
     return SIMULST_OK;
 }
 
-int simulst_mma_set_pipeline(int enable) {
-    g_use_pipe = enable ? 1 : 0;
+int simulst_mma_set_pipeline(int mode) {
+    if (mode < 0 || mode > 3) return SIMULST_E_ARG;
+    g_use_pipe = mode;
     return SIMULST_OK;
 }
 
@@ -100,7 +101,7 @@ int simulst_mma_train_fwd(const void* p_choose, int p_dtype, const void* soft_en
     prm.tma = g_use_tma && ((size_t)S * esz) % 16 == 0 && aligned(p_choose, 16) &&
               (!soft || aligned(soft_energy, 16));
     prm.vec_out = (S % 4 == 0) && aligned(alpha, 16) && (!soft || aligned(beta, 16));
-    prm.pipe = g_use_pipe;
+    prm.pipe = g_use_pipe & 1;
 
     const Config cfg = pick_config(S);
     const int mode = mode_of(flags, chunk_size);
@@ -147,7 +148,7 @@ int simulst_mma_train_bwd(const void* p_choose, int p_dtype, const void* soft_en
                      (!soft || aligned(grad_energy, 16));
     prm.tma = g_use_tma && ((size_t)S * esz) % 16 == 0 && a16;
     prm.vec_out = ((size_t)S * esz) % 16 == 0 && (S % 4 == 0) && a16;
-    prm.pipe = g_use_pipe;
+    prm.pipe = (g_use_pipe >> 1) & 1;
 
     const Config cfg = pick_config(S);
     const int mode = mode_of(flags, chunk_size);

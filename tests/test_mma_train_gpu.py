@@ -46,6 +46,17 @@ def assert_parity(got, ref, what="", ref64=None, extra_atol=0.0):
             f"(ref={float(ref.flatten()[idx]):.6e}, tensor scale={scale:.3e})")
 
 
+@pytest.fixture(params=[1, 3, 0], ids=["default", "pipelined", "generic"])
+def kernel_family(request):
+    """simulst_mma_set_pipeline mode: default (pipelined forward + generic backward), both
+    pipelined, both generic -- every family has to pass the same parity gate."""
+    from simulst_b200 import _lib
+    lib = _lib.load()
+    assert lib.simulst_mma_set_pipeline(request.param) == 0
+    yield request.param
+    lib.simulst_mma_set_pipeline(1)
+
+
 def _run(p, se, mask, mp, chunk, soft, g_alpha, g_beta, dtype=torch.float32):
     from simulst_b200 import ops
     dev = torch.device("cuda")
@@ -64,7 +75,7 @@ def _run(p, se, mask, mp, chunk, soft, g_alpha, g_beta, dtype=torch.float32):
 
 
 @pytest.mark.parametrize("name", list(TRAIN))
-def test_mma_train_matches_reference_golden(name):
+def test_mma_train_matches_reference_golden(name, kernel_family):
     c = TRAIN[name]
     n, t, s, masked, chunk, soft, mp = [int(v) for v in c.cfg]
     alpha, beta, gp, ge = _run(c.p, c.soft_energy, opt(c.mask), bool(mp), chunk, bool(soft),
@@ -106,7 +117,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("n,t,s,masked,chunk,cfg", CASES)
-def test_mma_train_matches_oracle(n, t, s, masked, chunk, cfg):
+def test_mma_train_matches_oracle(n, t, s, masked, chunk, cfg, kernel_family):
     from simulst_b200 import _lib
     lib = _lib.load()
     p, se, mask, ga, gb = _seeded(n, t, s, seed=100 + s + t, masked=masked)
@@ -164,7 +175,7 @@ def test_pipelined_and_generic_kernels_agree(masked, soft):
     p, se, mask, ga, gb = _seeded(3, 17, 1024, seed=11, masked=masked)
     outs = []
     try:
-        for pipe in (1, 0):
+        for pipe in (3, 0):
             lib.simulst_mma_set_pipeline(pipe)
             outs.append(_run(p, se if soft else None, mask, True, 0, soft, ga, gb if soft else None))
     finally:
