@@ -6,7 +6,7 @@ namespace simulst {
 
 static int g_cfg_threads = 0, g_cfg_vpt = 0;   // 0 = automatic
 static int g_use_tma = 1;
-static int g_use_pipe = 1;   // bit 0: pipelined forward, bit 1: pipelined backward
+static int g_use_pipe = 5;   // bit 0: pipelined forward, bit 1: pipelined backward, bit 2: dense fast-path backward
 
 struct Config { int threads, vpt; };
 
@@ -71,7 +71,7 @@ int simulst_mma_set_tma(int enable) {
 }
 
 int simulst_mma_set_pipeline(int mode) {
-    if (mode < 0 || mode > 3) return SIMULST_E_ARG;
+    if (mode < 0 || mode > 7) return SIMULST_E_ARG;
     g_use_pipe = mode;
     return SIMULST_OK;
 }
@@ -149,6 +149,7 @@ int simulst_mma_train_bwd(const void* p_choose, int p_dtype, const void* soft_en
     prm.tma = g_use_tma && ((size_t)S * esz) % 16 == 0 && a16;
     prm.vec_out = ((size_t)S * esz) % 16 == 0 && (S % 4 == 0) && a16;
     prm.pipe = (g_use_pipe >> 1) & 1;
+    prm.fast = (g_use_pipe >> 2) & 1;
 
     const Config cfg = pick_config(S);
     const int mode = mode_of(flags, chunk_size);

@@ -30,7 +30,7 @@ struct BwdPlan {
 };
 
 template <int THREADS, int VPT, typename T, int MODE, bool FULL>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 4 : 1)) mma_bwd_kernel(const MmaParams prm, const BwdPlan plan) {
+__global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : 1)) mma_bwd_kernel(const MmaParams prm, const BwdPlan plan) {
     constexpr int NW = THREADS / kWarp;
     constexpr bool SOFT = MODE != kModeHard;
     constexpr bool CHUNK = MODE == kModeSoftCk;

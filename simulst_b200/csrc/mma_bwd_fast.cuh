@@ -1,0 +1,699 @@
+// MMA training backward, dense fast path: same mathematics and the same six block-wide
+// exchanges per target step as mma_bwd.cuh (see its header for the derivation; SURVEY Appendix
+// A.2-A.4), specialised for the case the training shape hits -- no padding mask, the source row
+// fills the CTA exactly (S == THREADS*VPT), rows staged by TMA, hard or infinite-lookback soft
+// attention -- and written for instruction count, because that kernel is issue bound:
+//   * element-wise arithmetic on float2 pairs (FADD2 / FMUL2 / FFMA2: one issue slot per two
+//     source positions); only the thread-local scan chains stay scalar;
+//   * warp scans use the shuffle's own predicate (no lane compares, no selects), and the scans
+//     that share a barrier advance level by level in one asm block so their latencies overlap;
+//   * cross-warp offsets are formed with 0/1 float weights (FMUL + FFMA) instead of predicated
+//     adds, and clamp masks are 0/1 floats folded into the packed multiplies: the loop keeps no
+//     long-lived predicates (the generic kernel spends ~140 instructions per step on LOP3 /
+//     ISETP traffic spilling and re-deriving predicates);
+//   * the mass-preservation correction ok*g'_last is formed by every thread from the block
+//     totals of the e- and gR-scans (g'_last = gA_last + sum(gR)/(eps + sum(e))), so the
+//     recurrence needs ONE suffix scan (the generic kernel splits the term off by linearity and
+//     pays a second scan);
+//   * the arg-max search runs only in the thread that holds the row maximum.
+// Every floating-point operation that feeds a clamp mask (cp, s, z) is performed in the same
+// order as in the forward kernels, so the recomputed masks agree with the forward pass; without
+// mass preservation the results are bit-identical to mma_bwd_kernel.
+#pragma once
+
+#include "mma_bwd.cuh"
+#include "mma_scan.cuh"
+
+namespace simulst {
+
+constexpr int kFastMaxWarps = 8;
+
+// ---- fused warp-scan levels (shuffle predicate = "source lane exists")
+// x: prefix product, m: max over the warp
+template <int D>
+__device__ __forceinline__ void lvl_mul_max(float& x, float& m) {
+    asm volatile("{\n\t.reg .f32 t0, t1;\n\t.reg .pred q0;\n\t"
+        "shfl.sync.up.b32 t0|q0, %0, %2, 0, 0xffffffff;\n\t"
+        "shfl.sync.bfly.b32 t1, %1, %2, 31, 0xffffffff;\n\t"
+        "@q0 mul.rn.f32 %0, %0, t0;\n\t"
+        "max.f32 %1, %1, t1;\n\t}"
+        : "+f"(x), "+f"(m)
+        : "n"(D));
+}
+// a: prefix sum, b: suffix sum
+template <int D>
+__device__ __forceinline__ void lvl_up_dn(float& a, float& b) {
+    asm volatile("{\n\t.reg .f32 t0, t1;\n\t.reg .pred q0, q1;\n\t"
+        "shfl.sync.up.b32 t0|q0, %0, %2, 0, 0xffffffff;\n\t"
+        "shfl.sync.down.b32 t1|q1, %1, %2, 31, 0xffffffff;\n\t"
+        "@q0 add.rn.f32 %0, %0, t0;\n\t"
+        "@q1 add.rn.f32 %1, %1, t1;\n\t}"
+        : "+f"(a), "+f"(b)
+        : "n"(D));
+}
+// a, b: suffix sums
+template <int D>
+__device__ __forceinline__ void lvl_dn_dn(float& a, float& b) {
+    asm volatile("{\n\t.reg .f32 t0, t1;\n\t.reg .pred q0;\n\t"
+        "shfl.sync.down.b32 t0|q0, %0, %2, 31, 0xffffffff;\n\t"
+        "shfl.sync.down.b32 t1, %1, %2, 31, 0xffffffff;\n\t"
+        "@q0 add.rn.f32 %0, %0, t0;\n\t"
+        "@q0 add.rn.f32 %1, %1, t1;\n\t}"
+        : "+f"(a), "+f"(b)
+        : "n"(D));
+}
+// a: suffix sum (distance DA), s: butterfly sum (distance DS)
+template <int DA, int DS>
+__device__ __forceinline__ void lvl_dn_sum(float& a, float& s) {
+    asm volatile("{\n\t.reg .f32 t0, t1;\n\t.reg .pred q0;\n\t"
+        "shfl.sync.down.b32 t0|q0, %0, %2, 31, 0xffffffff;\n\t"
+        "shfl.sync.bfly.b32 t1, %1, %3, 31, 0xffffffff;\n\t"
+        "@q0 add.rn.f32 %0, %0, t0;\n\t"
+        "add.rn.f32 %1, %1, t1;\n\t}"
+        : "+f"(a), "+f"(s)
+        : "n"(DA), "n"(DS));
+}
+// value of the previous / next lane, `ident` at the warp edge
+__device__ __forceinline__ float nb_prev(float v, float ident) {
+    float o;
+    asm volatile("{\n\t.reg .pred q;\n\t"
+        "shfl.sync.up.b32 %0|q, %1, 1, 0, 0xffffffff;\n\t"
+        "@!q mov.f32 %0, %2;\n\t}"
+        : "=&f"(o)
+        : "f"(v), "f"(ident));
+    return o;
+}
+__device__ __forceinline__ float nb_next(float v, float ident) {
+    float o;
+    asm volatile("{\n\t.reg .pred q;\n\t"
+        "shfl.sync.down.b32 %0|q, %1, 1, 31, 0xffffffff;\n\t"
+        "@!q mov.f32 %0, %2;\n\t}"
+        : "=&f"(o)
+        : "f"(v), "f"(ident));
+    return o;
+}
+
+// ---- cross-warp combination with 0/1 float weights
+template <int NW>
+struct WarpWeights {
+    float lt[NW > 1 ? NW - 1 : 1];   // lt[w]   = 1 if w < warp      (w = 0 .. NW-2)
+    float gt[NW > 1 ? NW - 1 : 1];   // gt[w-1] = 1 if w > warp      (w = 1 .. NW-1)
+    __device__ __forceinline__ explicit WarpWeights(int warp) {
+#pragma unroll
+        for (int w = 0; w + 1 < NW; ++w) {
+            lt[w] = (w < warp) ? 1.0f : 0.0f;
+            gt[w] = (w + 1 > warp) ? 1.0f : 0.0f;
+        }
+        if (NW == 1) { lt[0] = 0.f; gt[0] = 0.f; }
+    }
+};
+template <int NW>
+__device__ __forceinline__ void load_totals(const float* __restrict__ wt, float (&t)[NW]) {
+    if constexpr (NW == 1) {
+        t[0] = wt[0];
+    } else if constexpr (NW == 2) {
+        const float2 v = *reinterpret_cast<const float2*>(wt);
+        t[0] = v.x; t[1] = v.y;
+    } else {
+#pragma unroll
+        for (int q = 0; q < NW / 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(wt + 4 * q);
+            t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+        }
+    }
+}
+// sum of the warp totals strictly before this warp (same association as combine_prefix)
+template <int NW>
+__device__ __forceinline__ float off_prefix(const float (&t)[NW], const WarpWeights<NW>& ww) {
+    if constexpr (NW == 1) return 0.f;
+    float acc = t[0] * ww.lt[0];
+#pragma unroll
+    for (int w = 1; w + 1 < NW; ++w) acc = __fmaf_rn(t[w], ww.lt[w], acc);
+    return acc;
+}
+template <int NW>
+__device__ __forceinline__ float sum_all(const float (&t)[NW]) {
+    float acc = t[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) acc += t[w];
+    return acc;
+}
+// sum of the warp totals strictly after this warp (same association as combine_suffix)
+template <int NW>
+__device__ __forceinline__ float off_suffix(const float (&t)[NW], const WarpWeights<NW>& ww) {
+    if constexpr (NW == 1) return 0.f;
+    float acc = t[NW - 1] * ww.gt[NW - 2];
+#pragma unroll
+    for (int w = NW - 2; w >= 1; --w) acc = __fmaf_rn(t[w], ww.gt[w - 1], acc);
+    return acc;
+}
+// product of the warp totals strictly before this warp
+template <int NW>
+__device__ __forceinline__ float off_prefix_mul(const float (&t)[NW], const WarpWeights<NW>& ww) {
+    if constexpr (NW == 1) return 1.0f;
+    float acc = __fmaf_rn(t[0], ww.lt[0], 1.0f - ww.lt[0]);
+#pragma unroll
+    for (int w = 1; w + 1 < NW; ++w) acc *= __fmaf_rn(t[w], ww.lt[w], 1.0f - ww.lt[w]);
+    return acc;
+}
+
+// 1[0 <= v <= 1] as a 0/1 float weight, exactly: v*(1-v) >= 0.  (1-v is exact next to 1, the
+// product cannot change sign by rounding, -0 passes like the reference's v >= 0, NaN fails.)
+// One packed FMA + one packed multiply per pair, then one FSET per element.
+__device__ __forceinline__ float2 unit_mask2(float2 v) {
+    const float2 w = mul2(v, fma2(v, f2(-1.0f), f2(1.0f)));
+    return make_float2(w.x >= 0.0f ? 1.0f : 0.0f, w.y >= 0.0f ? 1.0f : 0.0f);
+}
+
+// VPT consecutive elements of a staged shared-memory row as float2 pairs
+template <typename T, int VPT>
+__device__ __forceinline__ void lds_row2(const void* __restrict__ row, int j0, float2 (&out)[VPT / 2]) {
+    if constexpr (std::is_same<T, __nv_bfloat16>::value && VPT % 8 == 0) {
+        // bf16 -> fp32 is a 16-bit shift: one SHL / one LOP3 per element
+#pragma unroll
+        for (int q = 0; q < VPT / 8; ++q) {
+            const uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(row) + j0 + 8 * q);
+            out[4 * q + 0] = make_float2(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u));
+            out[4 * q + 1] = make_float2(__uint_as_float(w.y << 16), __uint_as_float(w.y & 0xffff0000u));
+            out[4 * q + 2] = make_float2(__uint_as_float(w.z << 16), __uint_as_float(w.z & 0xffff0000u));
+            out[4 * q + 3] = make_float2(__uint_as_float(w.w << 16), __uint_as_float(w.w & 0xffff0000u));
+        }
+    } else {
+        float tmp[VPT];
+        lds_row<T, VPT>(reinterpret_cast<const T*>(row), j0, tmp);
+#pragma unroll
+        for (int q = 0; q < VPT / 2; ++q) out[q] = make_float2(tmp[2 * q], tmp[2 * q + 1]);
+    }
+}
+
+// Shared-memory layout (compile-time): header (mbarriers + exchange area), a 3-deep ring of
+// stages {p, energy, grad_alpha, grad_beta} and a 4-deep ring of alpha rows.  The alpha row of
+// step i-1 is read by two consecutive iterations (as the recurrence input of step i, then as
+// the soft-attention weights alpha'_{i-1} of step i-1), hence the extra slot.
+template <int CAP, typename T, bool SOFT>
+struct FastLayout {
+    static constexpr int kHeader = 128 + 2 * kXSlots * kXStride * 4 + 128;
+    static constexpr int kTRow = (CAP * (int)sizeof(T) + 127) / 128 * 128;
+    static constexpr int kFRow = (CAP * 4 + 127) / 128 * 128;
+    static constexpr int kOffP = 0;
+    static constexpr int kOffE = kTRow;
+    static constexpr int kOffGA = kOffE + (SOFT ? kTRow : 0);
+    static constexpr int kOffGB = kOffGA + kFRow;
+    static constexpr int kStage = kOffGB + (SOFT ? kFRow : 0);
+    static constexpr int kStages = 3;
+    static constexpr int kAlphaSlots = 4;
+    static constexpr int kOffAlpha = kHeader + kStages * kStage;
+    static constexpr int kTotal = kOffAlpha + kAlphaSlots * kFRow;
+};
+
+template <int THREADS, int VPT, typename T, bool SOFT>
+__global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS * VPT <= 2048 ? 2 : 1)))
+mma_bwd_fast_kernel(const MmaParams prm) {
+    constexpr int NW = THREADS / kWarp;
+    constexpr int H = VPT / 2;
+    constexpr int B3 = SOFT ? 0 : 1;     // exchange buffer of phase X3 (phases alternate buffers; hard mode skips X2 and X4)
+    using L = FastLayout<THREADS * VPT, T, SOFT>;
+    constexpr int NS = L::kStages;
+    static_assert(NW <= kFastMaxWarps && VPT % 2 == 0, "fast path: at most 8 warps");
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    float* xraw = reinterpret_cast<float*>(smem + 128);     // [2 buffers][kXSlots][kXStride]
+    unsigned char* stage0 = smem + L::kHeader;
+    unsigned char* alpha0 = smem + L::kOffAlpha;
+    auto xs = [&](int buf, int slot) -> float* { return xraw + (buf * kXSlots + slot) * kXStride; };
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.x;
+    const int S = prm.S, T_len = prm.T;
+    const int j0 = tid * VPT;
+    const float eps = prm.eps;
+    const bool mp = (prm.flags & SIMULST_MMA_MASS_PRESERVATION) != 0u;
+    const bool has_ga = prm.g_alpha != nullptr;
+    const bool has_gb = SOFT && prm.g_beta != nullptr;
+    const bool mp_last = mp && tid == THREADS - 1;      // owner of the column mass preservation rewrites
+
+    const size_t row0 = (size_t)n * T_len * S;
+    T* gp_out = reinterpret_cast<T*>(prm.g_p) + row0;
+    T* ge_out = SOFT ? reinterpret_cast<T*>(prm.g_e) + row0 : nullptr;
+    const float* side = mp ? prm.side + (size_t)n * T_len * 2 : nullptr;
+
+    const WarpWeights<NW> ww(warp);
+    // weight of a column in the mass-preservation Jacobian: 0 for the rewritten column
+    const float w_lastcol = mp_last ? 0.0f : 1.0f;
+
+    constexpr int kIssuers = NW < 5 ? NW : 5;
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) mbar_init(&bars[s], kIssuers);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const unsigned t_bytes = (unsigned)(S * sizeof(T)), f_bytes = (unsigned)(S * 4);
+    // Producers: iteration q stages step i = T-1-q into stage q % 3 and alpha slot q % 4
+    // (alpha_{i-1}); the very first call also brings alpha'_{T-1} into alpha slot 3.  The five
+    // bulk copies are dealt round-robin to the warps (copy j -> lane 0 of warp j % NW) so no
+    // single warp carries the whole address arithmetic on the step's critical path; every
+    // issuing warp arrives on the stage barrier with the byte count of its own copies.
+    auto issue = [&](int q) {
+        if (lane == 0 && warp < kIssuers) {
+            const int i = T_len - 1 - q;
+            const int s = q % NS;
+            unsigned char* st = stage0 + s * L::kStage;
+            const size_t ro = row0 + (size_t)i * S;
+            const bool w_p = (0 % NW) == warp, w_e = SOFT && (1 % NW) == warp, w_a = (2 % NW) == warp,
+                       w_ga = has_ga && (3 % NW) == warp, w_gb = has_gb && (4 % NW) == warp;
+            const bool a_prev = w_a && i > 0, a_first = w_a && SOFT && q == 0;
+            const unsigned bytes = (w_p ? t_bytes : 0u) + (w_e ? t_bytes : 0u) + (a_prev ? f_bytes : 0u) +
+                                   (a_first ? f_bytes : 0u) + (w_ga ? f_bytes : 0u) + (w_gb ? f_bytes : 0u);
+            mbar_expect_tx(&bars[s], bytes);
+            if (w_p) tma_load_1d(st + L::kOffP, reinterpret_cast<const T*>(prm.p) + ro, t_bytes, &bars[s]);
+            if (w_e) tma_load_1d(st + L::kOffE, reinterpret_cast<const T*>(prm.e) + ro, t_bytes, &bars[s]);
+            if (a_prev) tma_load_1d(alpha0 + (q & 3) * L::kFRow, prm.alpha + ro - S, f_bytes, &bars[s]);
+            if (a_first) tma_load_1d(alpha0 + 3 * L::kFRow, prm.alpha + ro, f_bytes, &bars[s]);
+            if (w_ga) tma_load_1d(st + L::kOffGA, prm.g_alpha + ro, f_bytes, &bars[s]);
+            if (w_gb) tma_load_1d(st + L::kOffGB, prm.g_beta + ro, f_bytes, &bars[s]);
+        }
+    };
+    for (int q = 0; q < NS - 1 && q < T_len; ++q) issue(q);
+
+    const float one_eps = 1.0f + eps;
+    const float2 eps2 = f2(eps);
+    float2 carry[H];
+#pragma unroll
+    for (int q = 0; q < H; ++q) carry[q] = f2(0.f);
+
+    // mass-preservation side values (row sum of step i, raw last column of step i-1), fetched
+    // one iteration ahead so the global-load latency never sits on the step's critical path
+    float side_sum = 0.f, side_prev_last = 0.f;
+    if (mp) {
+        side_sum = side[2 * (T_len - 1) + 1];
+        if (T_len > 1) side_prev_last = side[2 * (T_len - 2)];
+    }
+
+    int s = 0;
+    unsigned parity = 0u;
+#pragma unroll 1
+    for (int qi = 0; qi < T_len; ++qi) {
+        const int i = T_len - 1 - qi;
+        if (qi + NS - 1 < T_len) issue(qi + NS - 1);
+        float side_sum_next = 0.f, side_prev_next = 0.f;
+        if (mp && i > 0) {
+            side_sum_next = side[2 * (i - 1) + 1];
+            if (i > 1) side_prev_next = side[2 * (i - 2)];
+        }
+        mbar_wait(&bars[s], parity);
+        const unsigned char* st = stage0 + s * L::kStage;
+        const unsigned char* a_prev_row = alpha0 + (qi & 3) * L::kFRow;          // alpha'_{i-1}
+        const unsigned char* a_cur_row = alpha0 + ((qi + 3) & 3) * L::kFRow;     // alpha'_i
+        if (++s == NS) { s = 0; parity ^= 1u; }
+
+        float2 p[H], E[H];
+        lds_row2<T, VPT>(st + L::kOffP, j0, p);
+        if (SOFT) lds_row2<T, VPT>(st + L::kOffE, j0, E);
+
+        // ================= X1: exclusive cumprod of (1-p)+eps ; row max of E
+        float2 cp[H];
+        float xtot, Emax = -INFINITY;
+        {
+            float2 x[H];
+#pragma unroll
+            for (int q = 0; q < H; ++q) x[q] = add2(fma2(p[q], f2(-1.0f), f2(1.0f)), eps2);
+            float run = x[0].x;
+            cp[0] = f2(1.0f, run);
+#pragma unroll
+            for (int q = 1; q < H; ++q) {
+                run *= x[q - 1].y; cp[q].x = run;
+                run *= x[q].x;     cp[q].y = run;
+            }
+            xtot = run * x[H - 1].y;
+        }
+        if (SOFT) {
+#pragma unroll
+            for (int q = 0; q < H; ++q) Emax = fmaxf(Emax, fmaxf(E[q].x, E[q].y));
+        }
+        float xinc = xtot, wmax = Emax;
+        if (SOFT) {
+            lvl_mul_max<1>(xinc, wmax); lvl_mul_max<2>(xinc, wmax); lvl_mul_max<4>(xinc, wmax);
+            lvl_mul_max<8>(xinc, wmax); lvl_mul_max<16>(xinc, wmax);
+        } else {
+            xinc = wscan_prefix_mul(xinc);
+        }
+        if (lane == 31) {
+            xs(0, 0)[warp] = xinc;
+            if (SOFT) xs(0, 1)[warp] = wmax;
+        }
+        const float xexc = nb_prev(xinc, 1.0f);
+        __syncthreads();
+        float m = 0.f;
+        float2 rc[H], P[H], pass[H];
+        {
+            float t[NW];
+            load_totals<NW>(xs(0, 0), t);
+            const float xoff = off_prefix_mul<NW>(t, ww);
+            if (SOFT) {
+                float tm[NW];
+                load_totals<NW>(xs(0, 1), tm);
+                m = tm[0];
+#pragma unroll
+                for (int w = 1; w < NW; ++w) m = fmaxf(m, tm[w]);
+            }
+            const float2 cbase = f2((one_eps * xoff) * xexc);
+#pragma unroll
+            for (int q = 0; q < H; ++q) {
+                cp[q] = mul2(cbase, cp[q]);
+                const float2 c = f2(fminf(fmaxf(cp[q].x, eps), 1.0f), fminf(fmaxf(cp[q].y, eps), 1.0f));
+                rc[q] = rcp2(c);
+                pass[q] = f2(c.x == cp[q].x ? 1.0f : 0.0f, c.y == cp[q].y ? 1.0f : 0.0f);   // 1[eps <= cp <= 1]
+                P[q] = mul2(p[q], cp[q]);
+            }
+        }
+
+        // ================= X2: D = eps + prefix(e) ; first index attaining the row max
+        float2 ex[H], exm[H], rD[H];
+        float rD_last = 0.f;
+        int amax = 0;
+        if (SOFT) {
+            float2 Dl[H];
+            const float2 nm = f2(-m), l2e = f2(kLog2e);
+            float etot = 0.f;
+#pragma unroll
+            for (int q = 0; q < H; ++q) {
+                const float2 tt = mul2(add2(E[q], nm), l2e);
+                exm[q] = f2(ex2_approx(tt.x), ex2_approx(tt.y));
+                ex[q] = add2(exm[q], eps2);
+            }
+#pragma unroll
+            for (int q = 0; q < H; ++q) {
+                etot += ex[q].x; Dl[q].x = etot;
+                etot += ex[q].y; Dl[q].y = etot;
+            }
+            // first thread holding the row maximum (the element is located at the end of the step)
+            const int cand = __reduce_min_sync(kFull, (Emax == m) ? tid : 0x7fffffff);
+            const float einc = wscan_prefix_add(etot);
+            if (lane == 31) {
+                xs(1, 0)[warp] = einc;
+                reinterpret_cast<int*>(xs(1, 1))[warp] = cand;
+            }
+            const float eexc = nb_prev(einc, 0.f);
+            __syncthreads();
+            {
+                const int* ci = reinterpret_cast<const int*>(xs(1, 1));
+                amax = ci[0];
+#pragma unroll
+                for (int w = 1; w < NW; ++w) amax = min(amax, ci[w]);
+            }
+            float t[NW];
+            load_totals<NW>(xs(1, 0), t);
+            const float2 ebase = f2(off_prefix<NW>(t, ww) + eexc);
+            if (mp) rD_last = fast_rcp(eps + sum_all<NW>(t));
+#pragma unroll
+            for (int q = 0; q < H; ++q) rD[q] = rcp2(add2(eps2, add2(ebase, Dl[q])));
+        }
+
+        // ================= X3: s = prefix(u) ; R = suffix(r)
+        float2 u[H], sfull[H], mz[H], r[H], R[H];
+        {
+            float2 sl[H], Rl[H];
+            float utot = 0.f, rtot = 0.f;
+            {
+                float2 am1[H];
+                if (i > 0) {
+                    lds_row2<float, VPT>(a_prev_row, j0, am1);
+                    // undo mass preservation on the stored row: the recurrence ran on the raw alpha
+                    if (mp_last) am1[H - 1].y = side_prev_last;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < H; ++q) am1[q] = f2((j0 + 2 * q == 0) ? 1.0f : 0.0f, 0.0f);
+                }
+#pragma unroll
+                for (int q = 0; q < H; ++q) u[q] = mul2(am1[q], rc[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < H; ++q) {
+                utot += u[q].x; sl[q].x = utot;
+                utot += u[q].y; sl[q].y = utot;
+            }
+            if (SOFT) {
+                {
+                    float2 a_cur[H];
+                    lds_row2<float, VPT>(a_cur_row, j0, a_cur);
+#pragma unroll
+                    for (int q = 0; q < H; ++q) r[q] = mul2(a_cur[q], rD[q]);
+                }
+                rtot = r[H - 1].y; Rl[H - 1].y = rtot;
+                rtot += r[H - 1].x; Rl[H - 1].x = rtot;
+#pragma unroll
+                for (int q = H - 2; q >= 0; --q) {
+                    rtot += r[q].y; Rl[q].y = rtot;
+                    rtot += r[q].x; Rl[q].x = rtot;
+                }
+            }
+            // from here on u only feeds gc = -carry*u*1[eps<=cp<=1]: fold the clamp mask in
+#pragma unroll
+            for (int q = 0; q < H; ++q) u[q] = mul2(u[q], pass[q]);
+            float uinc = utot, rinc = rtot;
+            if (SOFT) {
+                lvl_up_dn<1>(uinc, rinc); lvl_up_dn<2>(uinc, rinc); lvl_up_dn<4>(uinc, rinc);
+                lvl_up_dn<8>(uinc, rinc); lvl_up_dn<16>(uinc, rinc);
+            } else {
+                uinc = wscan_prefix_add(uinc);
+            }
+            if (lane == 31) xs(B3, 0)[warp] = uinc;
+            if (SOFT && lane == 0) xs(B3, 1)[warp] = rinc;
+            const float uexc = nb_prev(uinc, 0.f);
+            float rexc = 0.f;
+            if (SOFT) rexc = nb_next(rinc, 0.f);
+            __syncthreads();
+            float t[NW];
+            load_totals<NW>(xs(B3, 0), t);
+            const float2 ubase = f2(off_prefix<NW>(t, ww) + uexc);
+#pragma unroll
+            for (int q = 0; q < H; ++q) {
+                sfull[q] = add2(ubase, sl[q]);
+                mz[q] = unit_mask2(mul2(P[q], sfull[q]));
+            }
+            if (SOFT) {
+                float tr[NW];
+                load_totals<NW>(xs(B3, 1), tr);
+                const float2 rbase = f2(off_suffix<NW>(tr, ww) + rexc);
+#pragma unroll
+                for (int q = 0; q < H; ++q) R[q] = add2(rbase, Rl[q]);
+            }
+        }
+
+        // ================= X4: gr = prefix(gR) ; d/d alpha' = gr/D ; hD = gr*r/D (= -gD)
+        float2 gsoft[H], ge1[H], hD[H];
+        float g_all = 0.f;
+        if (SOFT) {
+            float2 grl[H], gB[H];
+            float gtot = 0.f;
+            if (has_gb) {
+                lds_row2<float, VPT>(st + L::kOffGB, j0, gB);
+            } else {
+#pragma unroll
+                for (int q = 0; q < H; ++q) gB[q] = f2(0.f);
+            }
+#pragma unroll
+            for (int q = 0; q < H; ++q) {
+                const float2 gb = mul2(gB[q], unit_mask2(mul2(ex[q], R[q])));
+                ge1[q] = mul2(gb, R[q]);
+                const float2 gR = mul2(gb, ex[q]);
+                gtot += gR.x; grl[q].x = gtot;
+                gtot += gR.y; grl[q].y = gtot;
+            }
+            const float ginc = wscan_prefix_add(gtot);
+            if (lane == 31) xs(1, 0)[warp] = ginc;
+            const float gexc = nb_prev(ginc, 0.f);
+            __syncthreads();
+            float t[NW];
+            load_totals<NW>(xs(1, 0), t);
+            const float2 gbase = f2(off_prefix<NW>(t, ww) + gexc);
+            if (mp) g_all = sum_all<NW>(t);
+#pragma unroll
+            for (int q = 0; q < H; ++q) {
+                gsoft[q] = mul2(add2(gbase, grl[q]), rD[q]);
+                hD[q] = mul2(gsoft[q], r[q]);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < H; ++q) { gsoft[q] = f2(0.f); ge1[q] = f2(0.f); hD[q] = f2(0.f); }
+        }
+
+        // ================= X5: gu = suffix(mz*P*g0) ; suffix(hD)
+        // mass preservation: ga_j = g'_j - ok*g'_last (rewritten column: 0); g'_last is formed
+        // from block totals every thread already holds
+        float2 gA[H];
+        float gA_last = 0.f;
+        if (has_ga) {
+            lds_row2<float, VPT>(st + L::kOffGA, j0, gA);
+            if (mp) gA_last = reinterpret_cast<const float*>(st + L::kOffGA)[S - 1];
+        } else {
+#pragma unroll
+            for (int q = 0; q < H; ++q) gA[q] = f2(0.f);
+        }
+        float okg = 0.f;
+        if (mp) {
+            const float ok = (side_sum >= 0.0f && side_sum <= 1.0f) ? 1.0f : 0.0f;
+            okg = ok * (gA_last + g_all * rD_last);
+        }
+        float2 g0[H], gu[H], gEm[H];
+        float gEsum = 0.f;
+        {
+            float2 Al[H], Hl[H];
+#pragma unroll
+            for (int q = 0; q < H; ++q) g0[q] = add2(gA[q], gsoft[q]);
+            if (mp_last) g0[H - 1].y = 0.f;
+            const float2 nokg = f2(-okg);
+#pragma unroll
+            for (int q = 0; q < H; ++q) {
+                g0[q] = add2(g0[q], carry[q]);
+                if (mp) {
+                    const float2 wv = (q == H - 1) ? f2(1.0f, w_lastcol) : f2(1.0f);
+                    g0[q] = fma2(wv, nokg, g0[q]);
+                }
+            }
+            float Atot = 0.f, Htot = 0.f;
+#pragma unroll
+            for (int q = H - 1; q >= 0; --q) {
+                const float2 Aq = mul2(mul2(mz[q], P[q]), g0[q]);
+                Atot += Aq.y; Al[q].y = Atot;
+                Atot += Aq.x; Al[q].x = Atot;
+                if (SOFT) {
+                    Htot += hD[q].y; Hl[q].y = Htot;
+                    Htot += hD[q].x; Hl[q].x = Htot;
+                }
+            }
+            float Ainc = Atot, Hinc = Htot;
+            if (SOFT) {
+                lvl_dn_dn<1>(Ainc, Hinc); lvl_dn_dn<2>(Ainc, Hinc); lvl_dn_dn<4>(Ainc, Hinc);
+                lvl_dn_dn<8>(Ainc, Hinc); lvl_dn_dn<16>(Ainc, Hinc);
+            } else {
+                Ainc = wscan_suffix_add(Ainc);
+            }
+            if (lane == 0) {
+                xs(0, 0)[warp] = Ainc;
+                if (SOFT) xs(0, 1)[warp] = Hinc;
+            }
+            const float Aexc = nb_next(Ainc, 0.f);
+            float Hexc = 0.f;
+            if (SOFT) Hexc = nb_next(Hinc, 0.f);
+            __syncthreads();
+            float t[NW];
+            load_totals<NW>(xs(0, 0), t);
+            const float2 Abase = f2(off_suffix<NW>(t, ww) + Aexc);
+#pragma unroll
+            for (int q = 0; q < H; ++q) gu[q] = add2(Abase, Al[q]);
+            if (SOFT) {
+                float th[NW];
+                load_totals<NW>(xs(0, 1), th);
+                const float2 Hbase = f2(off_suffix<NW>(th, ww) + Hexc);
+                const float2 neg1 = f2(-1.0f);
+#pragma unroll
+                for (int q = 0; q < H; ++q) {
+                    const float2 ge = fma2(add2(Hbase, Hl[q]), neg1, ge1[q]);      // ge1 + suffix(gD)
+                    gEm[q] = mul2(ge, exm[q]);
+                    gEsum += gEm[q].x;
+                    gEsum += gEm[q].y;
+                }
+            }
+        }
+
+        // ================= X6: gL = exclusive suffix of gA ; sum of gEm
+        float2 gPk[H], gAl[H];
+        float gAtot = 0.f;
+        {
+            const float2 neg1 = f2(-1.0f);
+#pragma unroll
+            for (int q = H - 1; q >= 0; --q) {
+                gPk[q] = mul2(mul2(mz[q], g0[q]), sfull[q]);
+                carry[q] = mul2(gu[q], rc[q]);                       // dL/d alpha_{i-1}
+                const float2 gcu = mul2(carry[q], u[q]);             // = -gc * 1[eps<=cp<=1]
+                const float2 gcp = fma2(gcu, neg1, mul2(gPk[q], p[q]));
+                const float2 gAk = mul2(gcp, cp[q]);
+                gAl[q].y = gAtot; gAtot += gAk.y;                    // exclusive local suffix
+                gAl[q].x = gAtot; gAtot += gAk.x;
+            }
+        }
+        float gAinc = gAtot, ws = gEsum;
+        if (SOFT) {
+            lvl_dn_sum<1, 16>(gAinc, ws); lvl_dn_sum<2, 8>(gAinc, ws); lvl_dn_sum<4, 4>(gAinc, ws);
+            lvl_dn_sum<8, 2>(gAinc, ws); lvl_dn_sum<16, 1>(gAinc, ws);
+        } else {
+            gAinc = wscan_suffix_add(gAinc);
+        }
+        if (lane == 0) {
+            xs(1, 0)[warp] = gAinc;
+            if (SOFT) xs(1, 1)[warp] = ws;
+        }
+        const float gAexc = nb_next(gAinc, 0.f);
+        // 1/((1-p)+eps), recomputed here to keep it out of the registers for the whole step
+        float2 rx[H];
+#pragma unroll
+        for (int q = 0; q < H; ++q) rx[q] = rcp2(add2(fma2(p[q], f2(-1.0f), f2(1.0f)), eps2));
+        __syncthreads();
+        {
+            float t[NW];
+            load_totals<NW>(xs(1, 0), t);
+            const float2 gLbase = f2(off_suffix<NW>(t, ww) + gAexc);
+            const float2 neg1 = f2(-1.0f);
+            float outp[VPT];
+#pragma unroll
+            for (int q = 0; q < H; ++q) {
+                const float2 gL = add2(gLbase, gAl[q]);
+                const float2 o = fma2(mul2(gL, rx[q]), neg1, mul2(gPk[q], cp[q]));
+                outp[2 * q] = o.x; outp[2 * q + 1] = o.y;
+            }
+            st_row_t<T, VPT, true>(gp_out + (size_t)i * S, j0, S, true, outp);
+        }
+        if (SOFT) {
+            float oute[VPT];
+#pragma unroll
+            for (int q = 0; q < H; ++q) { oute[2 * q] = gEm[q].x; oute[2 * q + 1] = gEm[q].y; }
+            if (amax == tid) {                  // one thread per row: autograd routes max's gradient to the arg-max
+                float tg[NW];
+                load_totals<NW>(xs(1, 1), tg);
+                const float gEall = sum_all<NW>(tg);
+                float2 Er[H];
+                lds_row2<T, VPT>(st + L::kOffE, j0, Er);
+                bool done = false;
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) {
+                    const bool hit = !done && SIMULST_EL(Er, k) == m;
+                    if (hit) oute[k] -= gEall;
+                    done = done || hit;
+                }
+            }
+            st_row_t<T, VPT, true>(ge_out + (size_t)i * S, j0, S, true, oute);
+        }
+        side_sum = side_sum_next;
+        side_prev_last = side_prev_next;
+    }
+}
+
+template <int THREADS, int VPT, typename T, bool SOFT>
+int launch_mma_bwd_fast(const MmaParams& prm, cudaStream_t stream) {
+    if constexpr (THREADS / kWarp > kFastMaxWarps || VPT % 8 != 0) {
+        return 1;
+    } else {
+        constexpr int CAP = THREADS * VPT;
+        using L = FastLayout<CAP, T, SOFT>;
+        // dense rows only: no mask, the row fills the CTA, TMA staging and 16-byte rows legal
+        if (prm.mask != nullptr || prm.S != CAP || !prm.vec_out || !prm.tma) return 1;
+        auto kern = mma_bwd_fast_kernel<THREADS, VPT, T, SOFT>;
+        static bool attr_set[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!attr_set[dev & 63]) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) {
+                cudaGetLastError();
+                return SIMULST_E_LAUNCH;
+            }
+            attr_set[dev & 63] = true;
+        }
+        kern<<<prm.N, THREADS, L::kTotal, stream>>>(prm);
+        return check_launch();
+    }
+}
+
+}  // namespace simulst

@@ -2,6 +2,7 @@
 // -DSIMULST_INST_DTYPE=0|1|2 so the three dtypes compile in parallel).
 #include "mma_bwd.cuh"
 #include "mma_bwd_pipe.cuh"
+#include "mma_bwd_fast.cuh"
 #include "mma_fwd_pipe.cuh"
 #include "mma_dispatch.h"
 
@@ -21,6 +22,11 @@ using InstT = __half;
 int INST_NAME(const MmaParams& prm, int mode, int threads, int vpt, cudaStream_t stream) {
 #define X(TH, VP)                                                                         \
     if (threads == TH && vpt == VP) {                                                     \
+        if (prm.fast && mode != kModeSoftCk) {                                            \
+            const int rc = mode == kModeHard ? launch_mma_bwd_fast<TH, VP, InstT, false>(prm, stream) \
+                                             : launch_mma_bwd_fast<TH, VP, InstT, true>(prm, stream); \
+            if (rc != 1) return rc;             /* 1 = row does not qualify for the dense fast path */ \
+        }                                                                                 \
         if constexpr (TH <= kPipeMaxThreads) {                                            \
             if (prm.tma && prm.pipe && mode != kModeSoftCk) {                             \
                 const int rc = mode == kModeHard ? launch_mma_bwd_pipe<TH, VP, InstT, false>(prm, stream) \

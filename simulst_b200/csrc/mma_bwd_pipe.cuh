@@ -49,7 +49,7 @@ struct BwdPipePlan {
 };
 
 template <int THREADS, int VPT, typename T, bool SOFT, bool FULL>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 4 : (THREADS <= 256 ? 2 : 1)))
+__global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS <= 256 ? 2 : 1)))
 mma_bwd_pipe_kernel(const MmaParams prm, const BwdPipePlan plan) {
     constexpr int NW = THREADS / kWarp;
     constexpr int H = VPT / 2;

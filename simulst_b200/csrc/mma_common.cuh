@@ -32,6 +32,7 @@ struct MmaParams {
     int tma;                // 1: rows staged by TMA bulk copies
     int vec_out;            // 1: fp32 rows may be accessed as float4
     int pipe;               // 1: software-pipelined kernels (hard / infinite lookback, needs tma)
+    int fast;               // 1: dense fast-path backward kernel when the row qualifies
 };
 
 // Double-buffered per-warp exchange area in shared memory.

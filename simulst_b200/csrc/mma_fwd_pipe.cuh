@@ -48,7 +48,7 @@ struct PipePlan {
 };
 
 template <int THREADS, int VPT, typename T, bool SOFT, bool FULL>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 4 : (THREADS <= 256 ? 2 : 1)))
+__global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS <= 256 ? 2 : 1)))
 mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
     constexpr int NW = THREADS / kWarp;
     constexpr int H = VPT / 2;

@@ -1,4 +1,5 @@
 """Development timing probe (not a test): C2-shaped fwd / bwd timings per kernel config."""
+import os
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -20,14 +21,14 @@ gp = torch.empty_like(p); ge = torch.empty_like(e)
 status = torch.zeros(1, dtype=torch.int32, device=dev)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 st = torch.cuda.current_stream().cuda_stream
-flags = 3
+flags = int(os.environ.get('FLAGS', '3'))
 
 def fwd():
     return lib.simulst_mma_train_fwd(p.data_ptr(), 1, e.data_ptr(), 1, None, alpha.data_ptr(), beta.data_ptr(),
                                      side.data_ptr(), N, T, S, 1e-6, 0, flags, status.data_ptr(), st)
 def bwd():
     return lib.simulst_mma_train_bwd(p.data_ptr(), 1, e.data_ptr(), 1, None, alpha.data_ptr(), side.data_ptr(),
-                                     ga.data_ptr(), gb.data_ptr(), gp.data_ptr(), 1, ge.data_ptr(), 1,
+                                     ga.data_ptr(), gb.data_ptr() if flags & 1 else None, gp.data_ptr(), 1, ge.data_ptr(), 1,
                                      N, T, S, 1e-6, 0, flags, st)
 
 def timeit(fn, reps=5):
@@ -42,13 +43,22 @@ def timeit(fn, reps=5):
 
 el = N * T * S
 import os
-for cfg in [(128, 8)]:
+cfgs = [tuple(map(int, c.split('x'))) for c in os.environ.get('CFGS', '128x8').split(',')]
+for cfg in cfgs:
     if cfg[0] * cfg[1] < S:
         continue
-    for tma in ([0, 1] if os.environ.get("BOTH") else [1]):
+    modes = [int(m) for m in os.environ["MODES"].split(",")] if os.environ.get("MODES") else ([0, 1, 2, 3] if os.environ.get("BOTH") else [1])
+    ref = None
+    for tma in modes:
         assert lib.simulst_mma_set_config(*cfg) == 0
         lib.simulst_mma_set_pipeline(tma)
-        fwd(); bwd(); torch.cuda.synchronize()
+        fwd(); gp.zero_(); ge.zero_(); bwd(); torch.cuda.synchronize()
+        if ref is None:
+            ref = (gp.float().clone(), ge.float().clone())
+        else:
+            dp = (gp.float() - ref[0]).abs().max().item(); de = (ge.float() - ref[1]).abs().max().item()
+            print(f"   vs first mode: max|d grad_p| {dp:.3e} (scale {ref[0].abs().max().item():.3e})  max|d grad_e| {de:.3e} (scale {ref[1].abs().max().item():.3e})"
+                  f"  equal: {torch.equal(gp.float(), ref[0])} {torch.equal(ge.float(), ref[1])}")
         f_min, f_med = timeit(fwd)
         b_min, b_med = timeit(bwd)
         print(f"cfg={cfg} pipe={tma}: fwd {f_med:8.1f} us ({el*12/f_med/1e3:7.1f} GB/s)  "

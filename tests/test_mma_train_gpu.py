@@ -46,15 +46,19 @@ def assert_parity(got, ref, what="", ref64=None, extra_atol=0.0):
             f"(ref={float(ref.flatten()[idx]):.6e}, tensor scale={scale:.3e})")
 
 
-@pytest.fixture(params=[1, 3, 0], ids=["default", "pipelined", "generic"])
+DEFAULT_PIPELINE = 5
+
+
+@pytest.fixture(params=[5, 1, 3, 0], ids=["default", "pipe-fwd+generic-bwd", "pipelined", "generic"])
 def kernel_family(request):
-    """simulst_mma_set_pipeline mode: default (pipelined forward + generic backward), both
-    pipelined, both generic -- every family has to pass the same parity gate."""
+    """simulst_mma_set_pipeline mode: default (pipelined forward + dense fast-path backward where
+    the row qualifies), pipelined forward + generic backward, both pipelined, both generic --
+    every family has to pass the same parity gate."""
     from simulst_b200 import _lib
     lib = _lib.load()
     assert lib.simulst_mma_set_pipeline(request.param) == 0
     yield request.param
-    lib.simulst_mma_set_pipeline(1)
+    lib.simulst_mma_set_pipeline(DEFAULT_PIPELINE)
 
 
 def _run(p, se, mask, mp, chunk, soft, g_alpha, g_beta, dtype=torch.float32):
@@ -160,7 +164,7 @@ def test_tma_and_cooperative_staging_agree():
             outs.append(_run(p, se, mask, True, 0, True, ga, gb))
     finally:
         lib.simulst_mma_set_tma(1)
-        lib.simulst_mma_set_pipeline(1)
+        lib.simulst_mma_set_pipeline(DEFAULT_PIPELINE)
     for a, b in zip(*outs):
         assert torch.equal(a, b)
 
@@ -179,13 +183,48 @@ def test_pipelined_and_generic_kernels_agree(masked, soft):
             lib.simulst_mma_set_pipeline(pipe)
             outs.append(_run(p, se if soft else None, mask, True, 0, soft, ga, gb if soft else None))
     finally:
-        lib.simulst_mma_set_pipeline(1)
+        lib.simulst_mma_set_pipeline(DEFAULT_PIPELINE)
     for a, b in zip(*outs):
         if a is None:
             assert b is None
             continue
         scale = float(b.abs().max())
         torch.testing.assert_close(a, b, rtol=5e-6, atol=5e-6 * scale)
+
+
+@pytest.mark.parametrize("shape", [(3, 17, 1024), (5, 9, 256), (4, 6, 512), (2, 5, 2048)])
+@pytest.mark.parametrize("soft", [False, True])
+@pytest.mark.parametrize("mp", [False, True])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fast_backward_matches_generic(shape, soft, mp, dtype):
+    """The dense fast-path backward (mma_bwd_fast.cuh) performs the generic kernel's arithmetic
+    in the same order: bit-identical without mass preservation; with it, the correction
+    ok*g'_last is formed from block totals (one rounding apart), so results agree to a few ulp."""
+    from simulst_b200 import _lib
+    lib = _lib.load()
+    n, t, s_len = shape
+    p, se, _, ga, gb = _seeded(n, t, s_len, seed=21, masked=False)
+    p, se = p.to(dtype), se.to(dtype)
+    outs = []
+    try:
+        for pipe in (4, 0):
+            lib.simulst_mma_set_pipeline(pipe)
+            outs.append(_run(p, se if soft else None, None, mp, 0, soft, ga, gb if soft else None, dtype=dtype))
+    finally:
+        lib.simulst_mma_set_pipeline(DEFAULT_PIPELINE)
+    for k, (a, b) in enumerate(zip(*outs)):
+        if a is None:
+            assert b is None
+            continue
+        if not mp or k < 2:
+            assert torch.equal(a, b), f"output {k}"
+        else:
+            # the generic kernel forms suffix(mz*P*g0) - ok*g'_last*suffix(mz*P) (two sums of the
+            # size of the incoming gradient, then a cancellation); the fast kernel subtracts
+            # first.  The difference is rounding at the scale of the incoming gradients.
+            scale = max(float(b.float().abs().max()), float(ga.abs().max()), float(gb.abs().max()) if soft else 0.0)
+            ulp = 2.0 ** -7 if dtype == torch.bfloat16 else 5e-6     # one 16-bit rounding step apart at most
+            torch.testing.assert_close(a.float(), b.float(), rtol=ulp, atol=2e-6 * scale)
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
