@@ -93,6 +93,23 @@ __device__ __forceinline__ float nb_next(float v, float ident) {
     return o;
 }
 
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0u;
+}
+// global load whose result the compiler treats as thread-varying (keeps a prefetched scalar in
+// a vector register instead of converting it to a uniform register -- and waiting -- at once)
+__device__ __forceinline__ float ldg_opaque(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // ---- cross-warp combination with 0/1 float weights
 template <int NW>
 struct WarpWeights {
@@ -223,7 +240,10 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     unsigned char* alpha0 = smem + L::kOffAlpha;
     auto xs = [&](int buf, int slot) -> float* { return xraw + (buf * kXSlots + slot) * kXStride; };
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // warp index through a shuffle: the compiler then knows it is warp-uniform (uniform registers,
+    // uniform branches around the TMA issue code)
+    const int warp = __shfl_sync(kFull, tid >> 5, 0);
     const int n = blockIdx.x;
     const int S = prm.S, T_len = prm.T;
     const int j0 = tid * VPT;
@@ -256,23 +276,30 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     // single warp carries the whole address arithmetic on the step's critical path; every
     // issuing warp arrives on the stage barrier with the byte count of its own copies.
     auto issue = [&](int q) {
-        if (lane == 0 && warp < kIssuers) {
-            const int i = T_len - 1 - q;
-            const int s = q % NS;
-            unsigned char* st = stage0 + s * L::kStage;
-            const size_t ro = row0 + (size_t)i * S;
-            const bool w_p = (0 % NW) == warp, w_e = SOFT && (1 % NW) == warp, w_a = (2 % NW) == warp,
-                       w_ga = has_ga && (3 % NW) == warp, w_gb = has_gb && (4 % NW) == warp;
-            const bool a_prev = w_a && i > 0, a_first = w_a && SOFT && q == 0;
-            const unsigned bytes = (w_p ? t_bytes : 0u) + (w_e ? t_bytes : 0u) + (a_prev ? f_bytes : 0u) +
-                                   (a_first ? f_bytes : 0u) + (w_ga ? f_bytes : 0u) + (w_gb ? f_bytes : 0u);
-            mbar_expect_tx(&bars[s], bytes);
-            if (w_p) tma_load_1d(st + L::kOffP, reinterpret_cast<const T*>(prm.p) + ro, t_bytes, &bars[s]);
-            if (w_e) tma_load_1d(st + L::kOffE, reinterpret_cast<const T*>(prm.e) + ro, t_bytes, &bars[s]);
-            if (a_prev) tma_load_1d(alpha0 + (q & 3) * L::kFRow, prm.alpha + ro - S, f_bytes, &bars[s]);
-            if (a_first) tma_load_1d(alpha0 + 3 * L::kFRow, prm.alpha + ro, f_bytes, &bars[s]);
-            if (w_ga) tma_load_1d(st + L::kOffGA, prm.g_alpha + ro, f_bytes, &bars[s]);
-            if (w_gb) tma_load_1d(st + L::kOffGB, prm.g_beta + ro, f_bytes, &bars[s]);
+        const int i = T_len - 1 - q;
+        const int s = q % NS;
+        unsigned char* st = stage0 + s * L::kStage;
+        uint64_t* bar = &bars[s];
+        const size_t ro = row0 + (size_t)i * S;
+#pragma unroll
+        for (int w = 0; w < kIssuers; ++w) {
+            if (warp == w) {                    // warp-uniform
+                if (elect_one()) {
+                    const bool c_p = (0 % NW) == w, c_e = SOFT && (1 % NW) == w, c_a = (2 % NW) == w,
+                               c_ga = (3 % NW) == w, c_gb = SOFT && (4 % NW) == w;      // compile-time
+                    const bool a_prev = c_a && i > 0, a_first = c_a && SOFT && q == 0;
+                    const bool l_ga = c_ga && has_ga, l_gb = c_gb && has_gb;
+                    const unsigned bytes = (c_p ? t_bytes : 0u) + (c_e ? t_bytes : 0u) + (a_prev ? f_bytes : 0u) +
+                                           (a_first ? f_bytes : 0u) + (l_ga ? f_bytes : 0u) + (l_gb ? f_bytes : 0u);
+                    mbar_expect_tx(bar, bytes);
+                    if (c_p) tma_load_1d(st + L::kOffP, reinterpret_cast<const T*>(prm.p) + ro, t_bytes, bar);
+                    if (c_e) tma_load_1d(st + L::kOffE, reinterpret_cast<const T*>(prm.e) + ro, t_bytes, bar);
+                    if (a_prev) tma_load_1d(alpha0 + (q & 3) * L::kFRow, prm.alpha + ro - S, f_bytes, bar);
+                    if (a_first) tma_load_1d(alpha0 + 3 * L::kFRow, prm.alpha + ro, f_bytes, bar);
+                    if (l_ga) tma_load_1d(st + L::kOffGA, prm.g_alpha + ro, f_bytes, bar);
+                    if (l_gb) tma_load_1d(st + L::kOffGB, prm.g_beta + ro, f_bytes, bar);
+                }
+            }
         }
     };
     for (int q = 0; q < NS - 1 && q < T_len; ++q) issue(q);
@@ -299,8 +326,8 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         if (qi + NS - 1 < T_len) issue(qi + NS - 1);
         float side_sum_next = 0.f, side_prev_next = 0.f;
         if (mp && i > 0) {
-            side_sum_next = side[2 * (i - 1) + 1];
-            if (i > 1) side_prev_next = side[2 * (i - 2)];
+            side_sum_next = ldg_opaque(side + 2 * (i - 1) + 1);
+            if (i > 1) side_prev_next = ldg_opaque(side + 2 * (i - 2));
         }
         mbar_wait(&bars[s], parity);
         const unsigned char* st = stage0 + s * L::kStage;
