@@ -331,8 +331,8 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config(world),
-            "roofline": {"bound": "hbm", "kernel": "mma_bwd_kernel", "achieved": ach, "peak": peak,
-                         "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic("mma_bwd_kernel"),
+            "roofline": {"bound": "hbm", "kernel": "mma_bwd_fast_kernel", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic("mma_bwd_fast_kernel"),
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": elems * BYTES_BWD,
                          "kernel_ms": bwd_ms,

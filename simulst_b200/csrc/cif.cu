@@ -35,6 +35,8 @@ cif_plan_kernel(const TA* __restrict__ alpha, const uint8_t* __restrict__ mask,
                 int64_t* __restrict__ lengths, int* __restrict__ t_max,
                 int* __restrict__ seg_first, int seg_stride, int S, float beta,
                 unsigned* status) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sm[];
     float* a = sm;
     float* scratch = sm + ((S + 1) / 2) * 2;       // 8-byte aligned: holds doubles
@@ -385,6 +387,8 @@ cif_bwd_alpha_kernel(const TA* __restrict__ alpha, const uint8_t* __restrict__ m
                      const float* __restrict__ scale, const float* __restrict__ alpha_sum,
                      const float* __restrict__ g_alpha_sum, const float* __restrict__ ws_gl,
                      const float* __restrict__ ws_gd, TA* __restrict__ g_alpha, int S, int training) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sm[];
     float* ga = sm;
     float* scratch = sm + S;
@@ -503,9 +507,8 @@ int simulst_cif_plan(const void* alpha, int a_dtype, const uint8_t* padding_mask
             cudaGetLastError();
             return (int)SIMULST_E_SHAPE;
         }
-        kern<<<B, kPlanThreads, smem, (cudaStream_t)stream>>>((const TA*)alpha, padding_mask, desired_sum,
-                                                           target_lengths, csum, scale, alpha_sum, lengths,
-                                                           t_max, seg_first, seg_stride, S, beta, status);
+        launch_pdl(kern, B, kPlanThreads, smem, (cudaStream_t)stream, (const TA*)alpha, padding_mask, desired_sum,
+                   target_lengths, csum, scale, alpha_sum, lengths, t_max, seg_first, seg_stride, S, beta, status);
         return check_launch();
     });
 }
@@ -538,7 +541,7 @@ int simulst_cif_fwd(const void* input, int x_dtype, const float* csum, const flo
                     auto kern = cif_fwd_tile_kernel<TX, TA, NP>;
                     if (int rc = set_smem(kern, smem)) return rc;
                     const unsigned grid = (unsigned)((long long)B * ((T_alloc + kTileWarps - 1) / kTileWarps));
-                    kern<<<grid, kTileThreads, smem, (cudaStream_t)stream>>>(
+                    launch_pdl(kern, grid, kTileThreads, smem, (cudaStream_t)stream,
                         (const TX*)input, csum, scale, (const TA*)alpha, padding_mask, seg_first, seg_stride,
                         (TX*)cif_out, (TX*)delays, tail_weights, lengths, lengths_out, t_max2, B, S, C, T,
                         T_alloc, beta, tail_thres, training, FC);
@@ -588,7 +591,7 @@ int simulst_cif_bwd(const void* input, int x_dtype, const float* csum, const flo
                     auto kern = cif_bwd_tile_kernel<TX, TA, NP>;
                     if (int rc2 = set_smem(kern, smem)) return rc2;
                     const unsigned grid = (unsigned)((long long)B * ((S + FR - 1) / FR));
-                    kern<<<grid, kTileThreads, smem, st>>>(
+                    launch_pdl(kern, grid, kTileThreads, smem, st,
                         (const TX*)input, csum, scale, (const TA*)alpha, padding_mask, (const TX*)grad_out,
                         (const TX*)grad_delays, tail_weights, lengths_before_tail, lengths_after_tail,
                         (TX*)grad_input, ws_gl, ws_gd, B, S, C, T, T_out, beta, tail_thres, training, FR, GR);
@@ -612,8 +615,8 @@ int simulst_cif_bwd(const void* input, int x_dtype, const float* csum, const flo
             cudaGetLastError();
             return (int)SIMULST_E_SHAPE;
         }
-        kern<<<B, kPlanThreads, smem, st>>>((const TA*)alpha, padding_mask, scale, alpha_sum, grad_alpha_sum,
-                                            ws_gl, ws_gd, (TA*)grad_alpha, S, training);
+        launch_pdl(kern, B, kPlanThreads, smem, st, (const TA*)alpha, padding_mask, scale, alpha_sum, grad_alpha_sum,
+                   ws_gl, ws_gd, (TA*)grad_alpha, S, training);
         return check_launch();
     });
 }

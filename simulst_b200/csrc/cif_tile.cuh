@@ -34,6 +34,8 @@ cif_bwd_tile_kernel(const TX* __restrict__ x, const float* __restrict__ csum, co
                     int B, int S, int C, int T, int T_out, float beta, float tail_thres, int training,
                     int FR, int GR) {
     constexpr int V = 4;
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);          // [0] x tile, [1] grad_out tile
     int* meta = reinterpret_cast<int*>(smem + 32);               // [0] first staged slot, [1] rows staged
@@ -183,6 +185,8 @@ cif_fwd_tile_kernel(const TX* __restrict__ x, const float* __restrict__ csum, co
                     int B, int S, int C, int T, int T_alloc, float beta, float tail_thres, int training,
                     int FC) {
     constexpr int V = 4;
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     TX* xt = reinterpret_cast<TX*>(smem + kTileHeader);

@@ -274,6 +274,15 @@ __device__ __forceinline__ void tma_store_wait_read() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// A kernel launched with launch_pdl() may start while its predecessor on the stream is still
+// draining: pdl_wait() blocks until every prerequisite grid has completed and its writes are
+// visible (no-op for a normal launch); pdl_launch_dependents() lets the successor's CTAs be
+// scheduled as soon as SM resources free up.  Every kernel launched this way calls pdl_wait()
+// before its first access to global memory.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ status word
 __device__ __forceinline__ void flag_status(unsigned* status, unsigned bits) {
     if (status != nullptr && bits != 0u) atomicOr(status, bits);
@@ -294,6 +303,22 @@ struct LaunchCounter {
         return v;
     }
 };
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                       Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);      // errors surface in check_launch()
+}
 
 inline int check_launch() {
     LaunchCounter::value() += 1;
