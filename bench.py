@@ -487,7 +487,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="row chunks of the host-buffer pipeline")
+    ap.add_argument("--e2e-chunks", type=int, default=16, help="row chunks of the host-buffer pipeline")
     ap.add_argument("--e2e-streams", type=int, default=2, help="compute streams of the host-buffer pipeline")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -40,6 +40,30 @@ __device__ __forceinline__ void lvl_mul_max(float& x, float& m) {
         : "+f"(x), "+f"(m)
         : "n"(D));
 }
+// x: prefix product, e: prefix sum (one shared shuffle predicate)
+template <int D>
+__device__ __forceinline__ void lvl_mul_add(float& x, float& e) {
+    asm volatile("{\n\t.reg .f32 t0, t1;\n\t.reg .pred q0;\n\t"
+        "shfl.sync.up.b32 t0|q0, %0, %2, 0, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 t1, %1, %2, 0, 0xffffffff;\n\t"
+        "@q0 mul.rn.f32 %0, %0, t0;\n\t"
+        "@q0 add.rn.f32 %1, %1, t1;\n\t}"
+        : "+f"(x), "+f"(e)
+        : "n"(D));
+}
+// a: suffix sum (distance DA), s: butterfly sum, m: butterfly max (distance DS)
+template <int DA, int DS>
+__device__ __forceinline__ void lvl_dn_sum_max(float& a, float& s, float& m) {
+    asm volatile("{\n\t.reg .f32 t0, t1, t2;\n\t.reg .pred q0;\n\t"
+        "shfl.sync.down.b32 t0|q0, %0, %3, 31, 0xffffffff;\n\t"
+        "shfl.sync.bfly.b32 t1, %1, %4, 31, 0xffffffff;\n\t"
+        "shfl.sync.bfly.b32 t2, %2, %4, 31, 0xffffffff;\n\t"
+        "@q0 add.rn.f32 %0, %0, t0;\n\t"
+        "add.rn.f32 %1, %1, t1;\n\t"
+        "max.f32 %2, %2, t2;\n\t}"
+        : "+f"(a), "+f"(s), "+f"(m)
+        : "n"(DA), "n"(DS));
+}
 // a: prefix sum, b: suffix sum
 template <int D>
 __device__ __forceinline__ void lvl_up_dn(float& a, float& b) {
@@ -93,15 +117,6 @@ __device__ __forceinline__ float nb_next(float v, float ident) {
     return o;
 }
 
-// one lane of the (converged) warp
-__device__ __forceinline__ bool elect_one() {
-    unsigned pred;
-    asm volatile("{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0u;
-}
 // global load whose result the compiler treats as thread-varying (keeps a prefetched scalar in
 // a vector register instead of converting it to a uniform register -- and waiting -- at once)
 __device__ __forceinline__ float ldg_opaque(const float* p) {
@@ -203,13 +218,40 @@ __device__ __forceinline__ void lds_row2(const void* __restrict__ row, int j0, f
     }
 }
 
+// max over VPT consecutive elements of a staged row; 16-bit rows are reduced with packed
+// 16-bit max instructions and converted once
+template <typename T, int VPT>
+__device__ __forceinline__ float lds_row_max(const void* __restrict__ row, int j0) {
+    if constexpr (sizeof(T) == 2 && VPT % 8 == 0) {
+        using T2 = typename std::conditional<std::is_same<T, __half>::value, __half2, __nv_bfloat162>::type;
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(row) + j0);
+        T2 acc;
+#pragma unroll
+        for (int q = 0; q < VPT / 8; ++q) {
+            const uint4 w = src[q];
+            const T2 a = __hmax2(*reinterpret_cast<const T2*>(&w.x), *reinterpret_cast<const T2*>(&w.y));
+            const T2 b = __hmax2(*reinterpret_cast<const T2*>(&w.z), *reinterpret_cast<const T2*>(&w.w));
+            const T2 c = __hmax2(a, b);
+            acc = q == 0 ? c : __hmax2(acc, c);
+        }
+        return fmaxf(to_f32<T>(acc.x), to_f32<T>(acc.y));
+    } else {
+        float2 v[VPT / 2];
+        lds_row2<T, VPT>(row, j0, v);
+        float m = fmaxf(v[0].x, v[0].y);
+#pragma unroll
+        for (int q = 1; q < VPT / 2; ++q) m = fmaxf(m, fmaxf(v[q].x, v[q].y));
+        return m;
+    }
+}
+
 // Shared-memory layout (compile-time): header (mbarriers + exchange area), a 3-deep ring of
 // stages {p, energy, grad_alpha, grad_beta} and a 4-deep ring of alpha rows.  The alpha row of
 // step i-1 is read by two consecutive iterations (as the recurrence input of step i, then as
 // the soft-attention weights alpha'_{i-1} of step i-1), hence the extra slot.
 template <int CAP, typename T, bool SOFT>
 struct FastLayout {
-    static constexpr int kHeader = 128 + 2 * kXSlots * kXStride * 4 + 128;
+    static constexpr int kHeader = 128 + 3 * kXSlots * kXStride * 4 + 128;      // mbarriers, 3 exchange buffers
     static constexpr int kTRow = (CAP * (int)sizeof(T) + 127) / 128 * 128;
     static constexpr int kFRow = (CAP * 4 + 127) / 128 * 128;
     static constexpr int kOffP = 0;
@@ -228,14 +270,16 @@ __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS
 mma_bwd_fast_kernel(const MmaParams prm) {
     constexpr int NW = THREADS / kWarp;
     constexpr int H = VPT / 2;
-    constexpr int B3 = SOFT ? 0 : 1;     // exchange buffer of phase X3 (phases alternate buffers; hard mode skips X2 and X4)
+    // exchange buffers per phase -- soft: X1 0, X3 1, X4 0, X5 1, X6 2 ; hard (no X4): X1 0, X3 1, X5 0, X6 1.
+    // A buffer is rewritten only after a barrier that follows its last read.
+    constexpr int B3 = 1, B4 = 0, B5 = SOFT ? 1 : 0, B6 = SOFT ? 2 : 1;
     using L = FastLayout<THREADS * VPT, T, SOFT>;
     constexpr int NS = L::kStages;
     static_assert(NW <= kFastMaxWarps && VPT % 2 == 0, "fast path: at most 8 warps");
 
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-    float* xraw = reinterpret_cast<float*>(smem + 128);     // [2 buffers][kXSlots][kXStride]
+    float* xraw = reinterpret_cast<float*>(smem + 128);     // [3 buffers][kXSlots][kXStride]
     unsigned char* stage0 = smem + L::kHeader;
     unsigned char* alpha0 = smem + L::kOffAlpha;
     auto xs = [&](int buf, int slot) -> float* { return xraw + (buf * kXSlots + slot) * kXStride; };
@@ -256,7 +300,12 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     const size_t row0 = (size_t)n * T_len * S;
     T* gp_out = reinterpret_cast<T*>(prm.g_p) + row0;
     T* ge_out = SOFT ? reinterpret_cast<T*>(prm.g_e) + row0 : nullptr;
-    const float* side = mp ? prm.side + (size_t)n * T_len * 2 : nullptr;
+    // (+ an opaque zero: the compiler must not treat the prefetched side values as uniform, or it
+    // converts them to uniform registers -- and waits for the load -- right at the loop top)
+    unsigned opaque_zero;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(opaque_zero));
+    opaque_zero >>= 5;
+    const float* side = mp ? prm.side + (size_t)n * T_len * 2 + opaque_zero : nullptr;
 
     const WarpWeights<NW> ww(warp);
     // weight of a column in the mass-preservation Jacobian: 0 for the rewritten column
@@ -318,6 +367,21 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         if (T_len > 1) side_prev_last = side[2 * (T_len - 2)];
     }
 
+    // row max of the first step's energies (every later one is reduced one iteration ahead)
+    float m_cur = 0.f, Emax_cur = -INFINITY;
+    if (SOFT) {
+        mbar_wait(&bars[0], 0u);
+        Emax_cur = lds_row_max<T, VPT>(stage0 + L::kOffE, j0);
+        const float wm = warp_max(Emax_cur);
+        if (lane == 0) xs(2, 2)[warp] = wm;
+        __syncthreads();
+        float tm[NW];
+        load_totals<NW>(xs(2, 2), tm);
+        m_cur = tm[0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) m_cur = fmaxf(m_cur, tm[w]);
+    }
+
     int s = 0;
     unsigned parity = 0u;
 #pragma unroll 1
@@ -339,9 +403,11 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         lds_row2<T, VPT>(st + L::kOffP, j0, p);
         if (SOFT) lds_row2<T, VPT>(st + L::kOffE, j0, E);
 
-        // ================= X1: exclusive cumprod of (1-p)+eps ; row max of E
+        // ================= X1: exclusive cumprod of (1-p)+eps ; D = eps + prefix(e) ; arg-max owner
+        // (the row maximum m_cur of this step's energies was reduced during the previous
+        // iteration's last exchange, so the product scan and the e-scan share one barrier)
         float2 cp[H];
-        float xtot, Emax = -INFINITY;
+        float xtot;
         {
             float2 x[H];
 #pragma unroll
@@ -355,55 +421,11 @@ mma_bwd_fast_kernel(const MmaParams prm) {
             }
             xtot = run * x[H - 1].y;
         }
+        float2 ex[H], exm[H], rD[H], Dl[H];
+        float etot = 0.f;
+        const float m = m_cur;
         if (SOFT) {
-#pragma unroll
-            for (int q = 0; q < H; ++q) Emax = fmaxf(Emax, fmaxf(E[q].x, E[q].y));
-        }
-        float xinc = xtot, wmax = Emax;
-        if (SOFT) {
-            lvl_mul_max<1>(xinc, wmax); lvl_mul_max<2>(xinc, wmax); lvl_mul_max<4>(xinc, wmax);
-            lvl_mul_max<8>(xinc, wmax); lvl_mul_max<16>(xinc, wmax);
-        } else {
-            xinc = wscan_prefix_mul(xinc);
-        }
-        if (lane == 31) {
-            xs(0, 0)[warp] = xinc;
-            if (SOFT) xs(0, 1)[warp] = wmax;
-        }
-        const float xexc = nb_prev(xinc, 1.0f);
-        __syncthreads();
-        float m = 0.f;
-        float2 rc[H], P[H], pass[H];
-        {
-            float t[NW];
-            load_totals<NW>(xs(0, 0), t);
-            const float xoff = off_prefix_mul<NW>(t, ww);
-            if (SOFT) {
-                float tm[NW];
-                load_totals<NW>(xs(0, 1), tm);
-                m = tm[0];
-#pragma unroll
-                for (int w = 1; w < NW; ++w) m = fmaxf(m, tm[w]);
-            }
-            const float2 cbase = f2((one_eps * xoff) * xexc);
-#pragma unroll
-            for (int q = 0; q < H; ++q) {
-                cp[q] = mul2(cbase, cp[q]);
-                const float2 c = f2(fminf(fmaxf(cp[q].x, eps), 1.0f), fminf(fmaxf(cp[q].y, eps), 1.0f));
-                rc[q] = rcp2(c);
-                pass[q] = f2(c.x == cp[q].x ? 1.0f : 0.0f, c.y == cp[q].y ? 1.0f : 0.0f);   // 1[eps <= cp <= 1]
-                P[q] = mul2(p[q], cp[q]);
-            }
-        }
-
-        // ================= X2: D = eps + prefix(e) ; first index attaining the row max
-        float2 ex[H], exm[H], rD[H];
-        float rD_last = 0.f;
-        int amax = 0;
-        if (SOFT) {
-            float2 Dl[H];
             const float2 nm = f2(-m), l2e = f2(kLog2e);
-            float etot = 0.f;
 #pragma unroll
             for (int q = 0; q < H; ++q) {
                 const float2 tt = mul2(add2(E[q], nm), l2e);
@@ -415,23 +437,53 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                 etot += ex[q].x; Dl[q].x = etot;
                 etot += ex[q].y; Dl[q].y = etot;
             }
+        }
+        float xinc = xtot, einc = etot;
+        if (SOFT) {
+            lvl_mul_add<1>(xinc, einc); lvl_mul_add<2>(xinc, einc); lvl_mul_add<4>(xinc, einc);
+            lvl_mul_add<8>(xinc, einc); lvl_mul_add<16>(xinc, einc);
+        } else {
+            xinc = wscan_prefix_mul(xinc);
+        }
+        if (SOFT) {
             // first thread holding the row maximum (the element is located at the end of the step)
-            const int cand = __reduce_min_sync(kFull, (Emax == m) ? tid : 0x7fffffff);
-            const float einc = wscan_prefix_add(etot);
+            const int cand = __reduce_min_sync(kFull, (Emax_cur == m) ? tid : 0x7fffffff);
             if (lane == 31) {
-                xs(1, 0)[warp] = einc;
-                reinterpret_cast<int*>(xs(1, 1))[warp] = cand;
+                xs(0, 1)[warp] = einc;
+                reinterpret_cast<int*>(xs(0, 2))[warp] = cand;
             }
-            const float eexc = nb_prev(einc, 0.f);
-            __syncthreads();
+        }
+        if (lane == 31) xs(0, 0)[warp] = xinc;
+        const float xexc = nb_prev(xinc, 1.0f);
+        float eexc = 0.f;
+        if (SOFT) eexc = nb_prev(einc, 0.f);
+        __syncthreads();
+        float2 rc[H], P[H], pass[H];
+        float rD_last = 0.f;
+        int amax = 0;
+        {
+            float t[NW];
+            load_totals<NW>(xs(0, 0), t);
+            const float xoff = off_prefix_mul<NW>(t, ww);
+            const float2 cbase = f2((one_eps * xoff) * xexc);
+#pragma unroll
+            for (int q = 0; q < H; ++q) {
+                cp[q] = mul2(cbase, cp[q]);
+                const float2 c = f2(fminf(fmaxf(cp[q].x, eps), 1.0f), fminf(fmaxf(cp[q].y, eps), 1.0f));
+                rc[q] = rcp2(c);
+                pass[q] = f2(c.x == cp[q].x ? 1.0f : 0.0f, c.y == cp[q].y ? 1.0f : 0.0f);   // 1[eps <= cp <= 1]
+                P[q] = mul2(p[q], cp[q]);
+            }
+        }
+        if (SOFT) {
             {
-                const int* ci = reinterpret_cast<const int*>(xs(1, 1));
+                const int* ci = reinterpret_cast<const int*>(xs(0, 2));
                 amax = ci[0];
 #pragma unroll
                 for (int w = 1; w < NW; ++w) amax = min(amax, ci[w]);
             }
             float t[NW];
-            load_totals<NW>(xs(1, 0), t);
+            load_totals<NW>(xs(0, 1), t);
             const float2 ebase = f2(off_prefix<NW>(t, ww) + eexc);
             if (mp) rD_last = fast_rcp(eps + sum_all<NW>(t));
 #pragma unroll
@@ -530,11 +582,11 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                 gtot += gR.y; grl[q].y = gtot;
             }
             const float ginc = wscan_prefix_add(gtot);
-            if (lane == 31) xs(1, 0)[warp] = ginc;
+            if (lane == 31) xs(B4, 0)[warp] = ginc;
             const float gexc = nb_prev(ginc, 0.f);
             __syncthreads();
             float t[NW];
-            load_totals<NW>(xs(1, 0), t);
+            load_totals<NW>(xs(B4, 0), t);
             const float2 gbase = f2(off_prefix<NW>(t, ww) + gexc);
             if (mp) g_all = sum_all<NW>(t);
 #pragma unroll
@@ -599,21 +651,21 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                 Ainc = wscan_suffix_add(Ainc);
             }
             if (lane == 0) {
-                xs(0, 0)[warp] = Ainc;
-                if (SOFT) xs(0, 1)[warp] = Hinc;
+                xs(B5, 0)[warp] = Ainc;
+                if (SOFT) xs(B5, 1)[warp] = Hinc;
             }
             const float Aexc = nb_next(Ainc, 0.f);
             float Hexc = 0.f;
             if (SOFT) Hexc = nb_next(Hinc, 0.f);
             __syncthreads();
             float t[NW];
-            load_totals<NW>(xs(0, 0), t);
+            load_totals<NW>(xs(B5, 0), t);
             const float2 Abase = f2(off_suffix<NW>(t, ww) + Aexc);
 #pragma unroll
             for (int q = 0; q < H; ++q) gu[q] = add2(Abase, Al[q]);
             if (SOFT) {
                 float th[NW];
-                load_totals<NW>(xs(0, 1), th);
+                load_totals<NW>(xs(B5, 1), th);
                 const float2 Hbase = f2(off_suffix<NW>(th, ww) + Hexc);
                 const float2 neg1 = f2(-1.0f);
 #pragma unroll
@@ -642,16 +694,23 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                 gAl[q].x = gAtot; gAtot += gAk.x;
             }
         }
-        float gAinc = gAtot, ws = gEsum;
+        // row max of the NEXT step's energies (its stage was requested two iterations ago)
+        float Emax_next = -INFINITY;
+        if (SOFT && i > 0) {
+            mbar_wait(&bars[s], parity);
+            Emax_next = lds_row_max<T, VPT>(stage0 + s * L::kStage + L::kOffE, j0);
+        }
+        float gAinc = gAtot, ws = gEsum, wmax = Emax_next;
         if (SOFT) {
-            lvl_dn_sum<1, 16>(gAinc, ws); lvl_dn_sum<2, 8>(gAinc, ws); lvl_dn_sum<4, 4>(gAinc, ws);
-            lvl_dn_sum<8, 2>(gAinc, ws); lvl_dn_sum<16, 1>(gAinc, ws);
+            lvl_dn_sum_max<1, 16>(gAinc, ws, wmax); lvl_dn_sum_max<2, 8>(gAinc, ws, wmax);
+            lvl_dn_sum_max<4, 4>(gAinc, ws, wmax); lvl_dn_sum_max<8, 2>(gAinc, ws, wmax);
+            lvl_dn_sum_max<16, 1>(gAinc, ws, wmax);
         } else {
             gAinc = wscan_suffix_add(gAinc);
         }
         if (lane == 0) {
-            xs(1, 0)[warp] = gAinc;
-            if (SOFT) xs(1, 1)[warp] = ws;
+            xs(B6, 0)[warp] = gAinc;
+            if (SOFT) { xs(B6, 1)[warp] = ws; xs(B6, 2)[warp] = wmax; }
         }
         const float gAexc = nb_next(gAinc, 0.f);
         // 1/((1-p)+eps), recomputed here to keep it out of the registers for the whole step
@@ -661,8 +720,17 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         __syncthreads();
         {
             float t[NW];
-            load_totals<NW>(xs(1, 0), t);
+            load_totals<NW>(xs(B6, 0), t);
             const float2 gLbase = f2(off_suffix<NW>(t, ww) + gAexc);
+            if (SOFT) {
+                float tm[NW];
+                load_totals<NW>(xs(B6, 2), tm);
+                float mn = tm[0];
+#pragma unroll
+                for (int w = 1; w < NW; ++w) mn = fmaxf(mn, tm[w]);
+                m_cur = mn;
+                Emax_cur = Emax_next;
+            }
             const float2 neg1 = f2(-1.0f);
             float outp[VPT];
 #pragma unroll
@@ -679,7 +747,7 @@ mma_bwd_fast_kernel(const MmaParams prm) {
             for (int q = 0; q < H; ++q) { oute[2 * q] = gEm[q].x; oute[2 * q + 1] = gEm[q].y; }
             if (amax == tid) {                  // one thread per row: autograd routes max's gradient to the arg-max
                 float tg[NW];
-                load_totals<NW>(xs(1, 1), tg);
+                load_totals<NW>(xs(B6, 1), tg);
                 const float gEall = sum_all<NW>(tg);
                 float2 Er[H];
                 lds_row2<T, VPT>(st + L::kOffE, j0, Er);

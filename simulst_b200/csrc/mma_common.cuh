@@ -46,10 +46,20 @@ struct Xchg {
     __device__ __forceinline__ void flip() { ++turn; }
 };
 
+// Elements per vector access of a thread's VPT consecutive elements: the largest power of two
+// that divides VPT and fits 16 bytes (VPT = 12 with 2-byte elements -> 4, i.e. 8-byte accesses:
+// the thread's base offset 24*tid bytes is only 8-byte aligned).
+template <typename T, int VPT>
+__host__ __device__ constexpr int row_pack() {
+    int pk = 16 / (int)sizeof(T);
+    while (pk > 1 && (VPT % pk) != 0) pk /= 2;
+    return pk;
+}
+
 // Read VPT consecutive elements of a staged row from shared memory in <=16-byte packs.
 template <typename T, int VPT>
 __device__ __forceinline__ void lds_row(const T* __restrict__ row, int j0, float (&out)[VPT]) {
-    constexpr int PK = (16 / sizeof(T)) < VPT ? (16 / sizeof(T)) : VPT;
+    constexpr int PK = row_pack<T, VPT>();
 #pragma unroll
     for (int q = 0; q < VPT / PK; ++q) {
         Pack<T, PK> pk = *reinterpret_cast<const Pack<T, PK>*>(row + j0 + q * PK);
@@ -95,7 +105,7 @@ __device__ __forceinline__ void ld_row_f32(const float* __restrict__ row, int j0
 template <typename T, int VPT, bool FULL = false>
 __device__ __forceinline__ void st_row_t(T* __restrict__ row, int j0, int S, bool vec,
                                          const float (&v)[VPT]) {
-    constexpr int PK = (16 / sizeof(T)) < VPT ? (16 / sizeof(T)) : VPT;
+    constexpr int PK = row_pack<T, VPT>();
 #pragma unroll
     for (int q = 0; q < VPT / PK; ++q) {
         const int j = j0 + q * PK;

@@ -51,6 +51,7 @@ template <int THREADS, int VPT, typename T, bool SOFT, bool FULL>
 __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS <= 256 ? 2 : 1)))
 mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
     constexpr int NW = THREADS / kWarp;
+    constexpr int kIssuers = (SOFT && NW > 1) ? 2 : 1;     // warps that issue TMA copies
     constexpr int H = VPT / 2;
     static_assert(VPT % 4 == 0, "VPT must be a multiple of 4");
 
@@ -61,7 +62,7 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
     unsigned char* stage0 = smem + plan.header_bytes();
     float4* stash = reinterpret_cast<float4*>(stage0 + (size_t)plan.n_stage * plan.rows * plan.row_bytes);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(kFull, tid >> 5, 0)   /* shuffle: known warp-uniform */;
     const int n = blockIdx.x;
     const int S = prm.S, T_len = prm.T;
     const int j0 = tid * VPT;
@@ -98,7 +99,7 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
     int last = S - 1;
 
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < NS; ++s) mbar_init(&bars[s], kIssuers);
         mbar_fence_init();
     }
     if (mp_add) {
@@ -124,14 +125,23 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
     const unsigned row_bytes = (unsigned)(S * sizeof(T));
     auto stage_p = [&](int s) { return reinterpret_cast<T*>(stage0 + (size_t)(s * plan.rows) * plan.row_bytes); };
     auto stage_e = [&](int s) { return reinterpret_cast<T*>(stage0 + (size_t)(s * plan.rows + 1) * plan.row_bytes); };
-    auto issue = [&](int i, int s) {      // called by thread 0 only
-        mbar_expect_tx(&bars[s], SOFT ? 2u * row_bytes : row_bytes);
-        tma_load_1d(stage_p(s), gp + (size_t)i * S, row_bytes, &bars[s]);
-        if (SOFT) tma_load_1d(stage_e(s), ge + (size_t)i * S, row_bytes, &bars[s]);
+    // one elected lane of warp 0 copies the p row, one of warp 1 (if there is one) the energy
+    // row; each arrives on the slot's barrier with its own byte count (warp-uniform branches)
+    auto issue = [&](int i, int s) {
+        if (warp == 0) {
+            if (elect_one()) {
+                mbar_expect_tx(&bars[s], (SOFT && kIssuers == 1) ? 2u * row_bytes : row_bytes);
+                tma_load_1d(stage_p(s), gp + (size_t)i * S, row_bytes, &bars[s]);
+                if (SOFT && kIssuers == 1) tma_load_1d(stage_e(s), ge + (size_t)i * S, row_bytes, &bars[s]);
+            }
+        } else if (SOFT && kIssuers == 2 && warp == 1) {
+            if (elect_one()) {
+                mbar_expect_tx(&bars[s], row_bytes);
+                tma_load_1d(stage_e(s), ge + (size_t)i * S, row_bytes, &bars[s]);
+            }
+        }
     };
-    if (tid == 0) {
-        for (int i = 0; i < NS && i < T_len; ++i) issue(i, i);
-    }
+    for (int i = 0; i < NS && i < T_len; ++i) issue(i, i);
 
     const float one_eps = 1.0f + eps;       // first element of the exclusive cumprod (functions.py:28-33)
     // state carried between iterations
@@ -269,7 +279,7 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
 
         __syncthreads();                    // ================================ the barrier
         // every thread has read ring slot `slotI`: refill it with the row NS steps ahead
-        if (tid == 0 && doI && it + 1 + NS < T_len) issue(it + 1 + NS, slotI);
+        if (doI && it + 1 + NS < T_len) issue(it + 1 + NS, slotI);
         if (++slotI == NS) { slotI = 0; parI ^= 1u; }
 
         // ================================================================ POST

@@ -37,6 +37,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 constexpr float kLog2e = 1.4426950408889634f;
 
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0u;
+}
+
 // ------------------------------------------------------------------ warp scans (predicated shuffles)
 // The asm statements are `volatile`: a pure asm may be sunk by the compiler into code that only
 // some lanes execute (it then wraps every shuffle in WARPSYNC.COLLECTIVE / ENDCOLLECTIVE).

@@ -227,9 +227,12 @@ def test_fast_backward_matches_generic(shape, soft, mp, dtype):
             torch.testing.assert_close(a.float(), b.float(), rtol=ulp, atol=2e-6 * scale)
 
 
+@pytest.mark.parametrize("shape", [(4, 12, 512), (2, 3, 4096), (2, 3, 6000)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-def test_half_inputs_match_oracle_fed_upcast_values(dtype):
-    p, se, mask, ga, gb = _seeded(4, 12, 512, seed=9)
+def test_half_inputs_match_oracle_fed_upcast_values(dtype, shape, kernel_family):
+    """16-bit inputs at every row-capacity class (8, 8 and 12 elements per thread: the last one
+    only allows 8-byte vector accesses for 2-byte elements)."""
+    p, se, mask, ga, gb = _seeded(*shape, seed=9)
     p_h, se_h = p.to(dtype), se.to(dtype)
     alpha, beta, gp, ge = _run(p_h, se_h, None, True, 0, True, ga, gb, dtype=dtype)
     p_o = p_h.float().requires_grad_()
