@@ -73,10 +73,12 @@ int simulst_mma_set_config(int threads, int vpt);
 /* 1 = stage rows with TMA bulk copies when alignment allows (default), 0 = cooperative loads */
 int simulst_mma_set_tma(int enable);
 /* Kernel choice for hard / infinite-lookback attention when rows can be TMA-staged.  Bit 0:
- * software-pipelined forward kernel, bit 1: software-pipelined backward kernel; a cleared bit
- * selects the generic (one scan per barrier) kernel.  Default 1: on B200 the pipelined forward is
- * 1.3x faster than the generic one, the pipelined backward 6 % slower.  Returns
- * 0 or E_ARG (mode outside 0..3). */
+ * software-pipelined forward kernel, bit 1: software-pipelined backward kernel, bit 2: dense
+ * fast-path backward kernel for unmasked rows that fill the CTA exactly (S = 256, 512, 1024,
+ * 2048; takes precedence over bit 1 when the row qualifies); cleared bits select the generic
+ * (one scan per barrier) kernels.  Default 5: on B200 the pipelined forward is 1.3x and the
+ * fast backward 1.4x faster than the generic kernels.  Returns 0 or E_ARG (mode
+ * outside 0..7). */
 int simulst_mma_set_pipeline(int mode);
 /* 1 = CIF forward/backward through the TMA-staged tile kernels when rows are 16-byte aligned
  * and C <= 512 (default), 0 = always the per-warp kernels (same results bit for bit) */
