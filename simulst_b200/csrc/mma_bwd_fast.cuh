@@ -26,7 +26,8 @@
 
 namespace simulst {
 
-constexpr int kFastMaxWarps = 8;
+constexpr int kFastMaxWarps = 16;          // CTA size limit of the fast path
+constexpr int kFastMaxWeightWarps = 8;    // up to here cross-warp offsets use 0/1 register weights
 
 // ---- fused warp-scan levels (shuffle predicate = "source lane exists")
 // x: prefix product, m: max over the warp
@@ -128,11 +129,13 @@ __device__ __forceinline__ float ldg_opaque(const float* p) {
 // ---- cross-warp combination with 0/1 float weights
 template <int NW>
 struct WarpWeights {
-    float lt[NW > 1 ? NW - 1 : 1];   // lt[w]   = 1 if w < warp      (w = 0 .. NW-2)
-    float gt[NW > 1 ? NW - 1 : 1];   // gt[w-1] = 1 if w > warp      (w = 1 .. NW-1)
+    static constexpr int kN = (NW > 1 && NW <= kFastMaxWeightWarps) ? NW - 1 : 1;
+    float lt[kN];   // lt[w]   = 1 if w < warp      (w = 0 .. NW-2)
+    float gt[kN];   // gt[w-1] = 1 if w > warp      (w = 1 .. NW-1)
     __device__ __forceinline__ explicit WarpWeights(int warp) {
+        if constexpr (NW > kFastMaxWeightWarps) { lt[0] = 0.f; gt[0] = 0.f; return; }
 #pragma unroll
-        for (int w = 0; w + 1 < NW; ++w) {
+        for (int w = 0; w + 1 < NW && w < kN; ++w) {
             lt[w] = (w < warp) ? 1.0f : 0.0f;
             gt[w] = (w + 1 > warp) ? 1.0f : 0.0f;
         }
@@ -187,6 +190,93 @@ __device__ __forceinline__ float off_prefix_mul(const float (&t)[NW], const Warp
 #pragma unroll
     for (int w = 1; w + 1 < NW; ++w) acc *= __fmaf_rn(t[w], ww.lt[w], 1.0f - ww.lt[w]);
     return acc;
+}
+
+// ---- block-level combination of the per-warp totals of one exchange slot.  Up to 8 warps:
+// every thread reads all totals (one or two LDS.128) and weights them; more warps: lane w of
+// every warp takes total w and the warp scans them with shuffles (the association of
+// combine_prefix / combine_suffix in common.cuh, so results match the generic kernels).
+template <int NW>
+__device__ __forceinline__ float xw_off_prefix(const float* __restrict__ wt, const WarpWeights<NW>& ww, int warp,
+                                               int lane, float* total) {
+    if constexpr (NW <= kFastMaxWeightWarps) {
+        float t[NW];
+        load_totals<NW>(wt, t);
+        if (total != nullptr) *total = sum_all<NW>(t);
+        return off_prefix<NW>(t, ww);
+    } else {
+        const float v = (lane < NW) ? wt[lane] : 0.f;
+        const float inc = wscan_prefix_add(v);
+        if (total != nullptr) *total = __shfl_sync(kFull, inc, NW - 1);
+        return __shfl_sync(kFull, inc - v, warp);
+    }
+}
+template <int NW>
+__device__ __forceinline__ float xw_off_suffix(const float* __restrict__ wt, const WarpWeights<NW>& ww, int warp, int lane) {
+    if constexpr (NW <= kFastMaxWeightWarps) {
+        float t[NW];
+        load_totals<NW>(wt, t);
+        return off_suffix<NW>(t, ww);
+    } else {
+        const float v = (lane < NW) ? wt[lane] : 0.f;
+        const float inc = wscan_suffix_add(v);
+        return __shfl_sync(kFull, inc - v, warp);
+    }
+}
+template <int NW>
+__device__ __forceinline__ float xw_off_prefix_mul(const float* __restrict__ wt, const WarpWeights<NW>& ww, int warp, int lane) {
+    if constexpr (NW <= kFastMaxWeightWarps) {
+        float t[NW];
+        load_totals<NW>(wt, t);
+        return off_prefix_mul<NW>(t, ww);
+    } else {
+        const float v = (lane < NW) ? wt[lane] : 1.0f;
+        const float inc = wscan_prefix_mul(v);
+        const float exc = nb_prev(inc, 1.0f);
+        return __shfl_sync(kFull, exc, warp);
+    }
+}
+template <int NW>
+__device__ __forceinline__ float fxw_sum(const float* __restrict__ wt, int lane) {
+    if constexpr (NW <= kFastMaxWeightWarps) {
+        float t[NW];
+        load_totals<NW>(wt, t);
+        return sum_all<NW>(t);
+    } else {
+        return warp_sum((lane < NW) ? wt[lane] : 0.f);
+    }
+}
+template <int NW>
+__device__ __forceinline__ float fxw_max(const float* __restrict__ wt, int lane) {
+    if constexpr (NW <= kFastMaxWeightWarps) {
+        float t[NW];
+        load_totals<NW>(wt, t);
+        float m = t[0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) m = fmaxf(m, t[w]);
+        return m;
+    } else {
+        return warp_max((lane < NW) ? wt[lane] : -INFINITY);
+    }
+}
+// sum of all totals, read by a single thread (no warp collectives)
+template <int NW>
+__device__ __forceinline__ float xw_sum_one(const float* __restrict__ wt) {
+    float acc = wt[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) acc += wt[w];
+    return acc;
+}
+template <int NW>
+__device__ __forceinline__ int xw_min_int(const int* __restrict__ wt, int lane) {
+    if constexpr (NW <= kFastMaxWeightWarps) {
+        int m = wt[0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) m = min(m, wt[w]);
+        return m;
+    } else {
+        return __reduce_min_sync(kFull, (lane < NW) ? wt[lane] : 0x7fffffff);
+    }
 }
 
 // 1[0 <= v <= 1] as a 0/1 float weight, exactly: v*(1-v) >= 0.  (1-v is exact next to 1, the
@@ -246,7 +336,7 @@ __device__ __forceinline__ float lds_row_max(const void* __restrict__ row, int j
 }
 
 // Shared-memory layout (compile-time): header (mbarriers + exchange area), a 3-deep ring of
-// stages {p, energy, grad_alpha, grad_beta} and a 4-deep ring of alpha rows.  The alpha row of
+// stages {p, energy, grad_alpha, grad_beta} and a (stages+1)-deep ring of alpha rows.  The alpha row of
 // step i-1 is read by two consecutive iterations (as the recurrence input of step i, then as
 // the soft-attention weights alpha'_{i-1} of step i-1), hence the extra slot.
 template <int CAP, typename T, bool SOFT>
@@ -259,13 +349,19 @@ struct FastLayout {
     static constexpr int kOffGA = kOffE + (SOFT ? kTRow : 0);
     static constexpr int kOffGB = kOffGA + kFRow;
     static constexpr int kStage = kOffGB + (SOFT ? kFRow : 0);
-    static constexpr int kStages = 3;
-    static constexpr int kAlphaSlots = 4;
+    // 3 stages (copies issued two steps ahead) when that fits the 227 KB of an SM, else 2
+    static constexpr int kStages = (kHeader + 3 * kStage + 4 * kFRow <= 227 * 1024) ? 3 : 2;
+    static constexpr int kAlphaSlots = kStages + 1;
     static constexpr int kOffAlpha = kHeader + kStages * kStage;
     static constexpr int kTotal = kOffAlpha + kAlphaSlots * kFRow;
 };
 
-template <int THREADS, int VPT, typename T, bool SOFT>
+// RAGGED: S < THREADS*VPT with S a multiple of VPT (every thread is wholly inside or wholly
+// outside the row).  The tails [S, CAP) of all ring slots are initialised once to neutral values
+// (p = 0, energy = -inf, alpha = grads = 0) -- the bulk copies only ever write [0, S) -- so the
+// step loop needs no per-element bounds checks: outside threads compute on neutral data, their
+// e-term is zeroed by one multiply, and they skip the stores.
+template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED>
 __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS * VPT <= 2048 ? 2 : 1)))
 mma_bwd_fast_kernel(const MmaParams prm) {
     constexpr int NW = THREADS / kWarp;
@@ -275,7 +371,8 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     constexpr int B3 = 1, B4 = 0, B5 = SOFT ? 1 : 0, B6 = SOFT ? 2 : 1;
     using L = FastLayout<THREADS * VPT, T, SOFT>;
     constexpr int NS = L::kStages;
-    static_assert(NW <= kFastMaxWarps && VPT % 2 == 0, "fast path: at most 8 warps");
+    constexpr int NA = L::kAlphaSlots;
+    static_assert(NW <= kFastMaxWarps && VPT % 4 == 0, "fast path: at most 16 warps");
 
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -295,7 +392,8 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     const bool mp = (prm.flags & SIMULST_MMA_MASS_PRESERVATION) != 0u;
     const bool has_ga = prm.g_alpha != nullptr;
     const bool has_gb = SOFT && prm.g_beta != nullptr;
-    const bool mp_last = mp && tid == THREADS - 1;      // owner of the column mass preservation rewrites
+    const bool inside = !RAGGED || j0 < S;              // this thread's VPT columns exist
+    const bool mp_last = mp && j0 + VPT == S;           // owner of the column mass preservation rewrites
 
     const size_t row0 = (size_t)n * T_len * S;
     T* gp_out = reinterpret_cast<T*>(prm.g_p) + row0;
@@ -315,6 +413,23 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) mbar_init(&bars[s], kIssuers);
         mbar_fence_init();
+    }
+    if (RAGGED && !inside) {
+        // neutral tails (never overwritten by the bulk copies)
+        const T ninf = from_f32<T>(-INFINITY), zero = from_f32<T>(0.f);
+        for (int st_i = 0; st_i < NS; ++st_i) {
+            unsigned char* st = stage0 + st_i * L::kStage;
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) {
+                reinterpret_cast<T*>(st + L::kOffP)[j0 + k] = zero;
+                if (SOFT) reinterpret_cast<T*>(st + L::kOffE)[j0 + k] = ninf;
+                reinterpret_cast<float*>(st + L::kOffGA)[j0 + k] = 0.f;
+                if (SOFT) reinterpret_cast<float*>(st + L::kOffGB)[j0 + k] = 0.f;
+            }
+        }
+        for (int a_i = 0; a_i < NA; ++a_i)
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) reinterpret_cast<float*>(alpha0 + a_i * L::kFRow)[j0 + k] = 0.f;
     }
     __syncthreads();
 
@@ -343,8 +458,8 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                     mbar_expect_tx(bar, bytes);
                     if (c_p) tma_load_1d(st + L::kOffP, reinterpret_cast<const T*>(prm.p) + ro, t_bytes, bar);
                     if (c_e) tma_load_1d(st + L::kOffE, reinterpret_cast<const T*>(prm.e) + ro, t_bytes, bar);
-                    if (a_prev) tma_load_1d(alpha0 + (q & 3) * L::kFRow, prm.alpha + ro - S, f_bytes, bar);
-                    if (a_first) tma_load_1d(alpha0 + 3 * L::kFRow, prm.alpha + ro, f_bytes, bar);
+                    if (a_prev) tma_load_1d(alpha0 + (q % NA) * L::kFRow, prm.alpha + ro - S, f_bytes, bar);
+                    if (a_first) tma_load_1d(alpha0 + (NA - 1) * L::kFRow, prm.alpha + ro, f_bytes, bar);
                     if (l_ga) tma_load_1d(st + L::kOffGA, prm.g_alpha + ro, f_bytes, bar);
                     if (l_gb) tma_load_1d(st + L::kOffGB, prm.g_beta + ro, f_bytes, bar);
                 }
@@ -355,6 +470,8 @@ mma_bwd_fast_kernel(const MmaParams prm) {
 
     const float one_eps = 1.0f + eps;
     const float2 eps2 = f2(eps);
+    const float in_f = inside ? 1.0f : 0.0f;
+    (void)in_f;
     float2 carry[H];
 #pragma unroll
     for (int q = 0; q < H; ++q) carry[q] = f2(0.f);
@@ -375,14 +492,10 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         const float wm = warp_max(Emax_cur);
         if (lane == 0) xs(2, 2)[warp] = wm;
         __syncthreads();
-        float tm[NW];
-        load_totals<NW>(xs(2, 2), tm);
-        m_cur = tm[0];
-#pragma unroll
-        for (int w = 1; w < NW; ++w) m_cur = fmaxf(m_cur, tm[w]);
+        m_cur = fxw_max<NW>(xs(2, 2), lane);
     }
 
-    int s = 0;
+    int s = 0, a_slot = 0;
     unsigned parity = 0u;
 #pragma unroll 1
     for (int qi = 0; qi < T_len; ++qi) {
@@ -395,9 +508,10 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         }
         mbar_wait(&bars[s], parity);
         const unsigned char* st = stage0 + s * L::kStage;
-        const unsigned char* a_prev_row = alpha0 + (qi & 3) * L::kFRow;          // alpha'_{i-1}
-        const unsigned char* a_cur_row = alpha0 + ((qi + 3) & 3) * L::kFRow;     // alpha'_i
+        const unsigned char* a_prev_row = alpha0 + a_slot * L::kFRow;                               // alpha'_{i-1}
+        const unsigned char* a_cur_row = alpha0 + (a_slot == 0 ? NA - 1 : a_slot - 1) * L::kFRow;   // alpha'_i
         if (++s == NS) { s = 0; parity ^= 1u; }
+        if (++a_slot == NA) a_slot = 0;
 
         float2 p[H], E[H];
         lds_row2<T, VPT>(st + L::kOffP, j0, p);
@@ -431,6 +545,7 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                 const float2 tt = mul2(add2(E[q], nm), l2e);
                 exm[q] = f2(ex2_approx(tt.x), ex2_approx(tt.y));
                 ex[q] = add2(exm[q], eps2);
+                if (RAGGED) ex[q] = mul2(ex[q], f2(in_f));       // no eps from columns beyond the row
             }
 #pragma unroll
             for (int q = 0; q < H; ++q) {
@@ -462,9 +577,7 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         float rD_last = 0.f;
         int amax = 0;
         {
-            float t[NW];
-            load_totals<NW>(xs(0, 0), t);
-            const float xoff = off_prefix_mul<NW>(t, ww);
+            const float xoff = xw_off_prefix_mul<NW>(xs(0, 0), ww, warp, lane);
             const float2 cbase = f2((one_eps * xoff) * xexc);
 #pragma unroll
             for (int q = 0; q < H; ++q) {
@@ -476,16 +589,10 @@ mma_bwd_fast_kernel(const MmaParams prm) {
             }
         }
         if (SOFT) {
-            {
-                const int* ci = reinterpret_cast<const int*>(xs(0, 2));
-                amax = ci[0];
-#pragma unroll
-                for (int w = 1; w < NW; ++w) amax = min(amax, ci[w]);
-            }
-            float t[NW];
-            load_totals<NW>(xs(0, 1), t);
-            const float2 ebase = f2(off_prefix<NW>(t, ww) + eexc);
-            if (mp) rD_last = fast_rcp(eps + sum_all<NW>(t));
+            amax = xw_min_int<NW>(reinterpret_cast<const int*>(xs(0, 2)), lane);
+            float e_all = 0.f;
+            const float2 ebase = f2(xw_off_prefix<NW>(xs(0, 1), ww, warp, lane, mp ? &e_all : nullptr) + eexc);
+            if (mp) rD_last = fast_rcp(eps + e_all);
 #pragma unroll
             for (int q = 0; q < H; ++q) rD[q] = rcp2(add2(eps2, add2(ebase, Dl[q])));
         }
@@ -544,18 +651,14 @@ mma_bwd_fast_kernel(const MmaParams prm) {
             float rexc = 0.f;
             if (SOFT) rexc = nb_next(rinc, 0.f);
             __syncthreads();
-            float t[NW];
-            load_totals<NW>(xs(B3, 0), t);
-            const float2 ubase = f2(off_prefix<NW>(t, ww) + uexc);
+            const float2 ubase = f2(xw_off_prefix<NW>(xs(B3, 0), ww, warp, lane, nullptr) + uexc);
 #pragma unroll
             for (int q = 0; q < H; ++q) {
                 sfull[q] = add2(ubase, sl[q]);
                 mz[q] = unit_mask2(mul2(P[q], sfull[q]));
             }
             if (SOFT) {
-                float tr[NW];
-                load_totals<NW>(xs(B3, 1), tr);
-                const float2 rbase = f2(off_suffix<NW>(tr, ww) + rexc);
+                const float2 rbase = f2(xw_off_suffix<NW>(xs(B3, 1), ww, warp, lane) + rexc);
 #pragma unroll
                 for (int q = 0; q < H; ++q) R[q] = add2(rbase, Rl[q]);
             }
@@ -585,10 +688,7 @@ mma_bwd_fast_kernel(const MmaParams prm) {
             if (lane == 31) xs(B4, 0)[warp] = ginc;
             const float gexc = nb_prev(ginc, 0.f);
             __syncthreads();
-            float t[NW];
-            load_totals<NW>(xs(B4, 0), t);
-            const float2 gbase = f2(off_prefix<NW>(t, ww) + gexc);
-            if (mp) g_all = sum_all<NW>(t);
+            const float2 gbase = f2(xw_off_prefix<NW>(xs(B4, 0), ww, warp, lane, mp ? &g_all : nullptr) + gexc);
 #pragma unroll
             for (int q = 0; q < H; ++q) {
                 gsoft[q] = mul2(add2(gbase, grl[q]), rD[q]);
@@ -658,15 +758,11 @@ mma_bwd_fast_kernel(const MmaParams prm) {
             float Hexc = 0.f;
             if (SOFT) Hexc = nb_next(Hinc, 0.f);
             __syncthreads();
-            float t[NW];
-            load_totals<NW>(xs(B5, 0), t);
-            const float2 Abase = f2(off_suffix<NW>(t, ww) + Aexc);
+            const float2 Abase = f2(xw_off_suffix<NW>(xs(B5, 0), ww, warp, lane) + Aexc);
 #pragma unroll
             for (int q = 0; q < H; ++q) gu[q] = add2(Abase, Al[q]);
             if (SOFT) {
-                float th[NW];
-                load_totals<NW>(xs(B5, 1), th);
-                const float2 Hbase = f2(off_suffix<NW>(th, ww) + Hexc);
+                const float2 Hbase = f2(xw_off_suffix<NW>(xs(B5, 1), ww, warp, lane) + Hexc);
                 const float2 neg1 = f2(-1.0f);
 #pragma unroll
                 for (int q = 0; q < H; ++q) {
@@ -713,22 +809,25 @@ mma_bwd_fast_kernel(const MmaParams prm) {
             if (SOFT) { xs(B6, 1)[warp] = ws; xs(B6, 2)[warp] = wmax; }
         }
         const float gAexc = nb_next(gAinc, 0.f);
+        // the thread owning the arg-max locates the element now: after the barrier below other
+        // warps may already refill this stage
+        int k_hit = -1;
+        if (SOFT && amax == tid) {
+            float2 Er[H];
+            lds_row2<T, VPT>(st + L::kOffE, j0, Er);
+#pragma unroll
+            for (int k = VPT - 1; k >= 0; --k)
+                if (SIMULST_EL(Er, k) == m) k_hit = k;
+        }
         // 1/((1-p)+eps), recomputed here to keep it out of the registers for the whole step
         float2 rx[H];
 #pragma unroll
         for (int q = 0; q < H; ++q) rx[q] = rcp2(add2(fma2(p[q], f2(-1.0f), f2(1.0f)), eps2));
         __syncthreads();
         {
-            float t[NW];
-            load_totals<NW>(xs(B6, 0), t);
-            const float2 gLbase = f2(off_suffix<NW>(t, ww) + gAexc);
+            const float2 gLbase = f2(xw_off_suffix<NW>(xs(B6, 0), ww, warp, lane) + gAexc);
             if (SOFT) {
-                float tm[NW];
-                load_totals<NW>(xs(B6, 2), tm);
-                float mn = tm[0];
-#pragma unroll
-                for (int w = 1; w < NW; ++w) mn = fmaxf(mn, tm[w]);
-                m_cur = mn;
+                m_cur = fxw_max<NW>(xs(B6, 2), lane);
                 Emax_cur = Emax_next;
             }
             const float2 neg1 = f2(-1.0f);
@@ -739,55 +838,57 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                 const float2 o = fma2(mul2(gL, rx[q]), neg1, mul2(gPk[q], cp[q]));
                 outp[2 * q] = o.x; outp[2 * q + 1] = o.y;
             }
-            st_row_t<T, VPT, true>(gp_out + (size_t)i * S, j0, S, true, outp);
+            if (inside) st_row_t<T, VPT, true>(gp_out + (size_t)i * S, j0, S, true, outp);
         }
         if (SOFT) {
             float oute[VPT];
 #pragma unroll
             for (int q = 0; q < H; ++q) { oute[2 * q] = gEm[q].x; oute[2 * q + 1] = gEm[q].y; }
-            if (amax == tid) {                  // one thread per row: autograd routes max's gradient to the arg-max
-                float tg[NW];
-                load_totals<NW>(xs(B6, 1), tg);
-                const float gEall = sum_all<NW>(tg);
-                float2 Er[H];
-                lds_row2<T, VPT>(st + L::kOffE, j0, Er);
-                bool done = false;
+            if (k_hit >= 0) {                   // one thread per row: autograd routes max's gradient to the arg-max
+                const float gEall = xw_sum_one<NW>(xs(B6, 1));
 #pragma unroll
-                for (int k = 0; k < VPT; ++k) {
-                    const bool hit = !done && SIMULST_EL(Er, k) == m;
-                    if (hit) oute[k] -= gEall;
-                    done = done || hit;
-                }
+                for (int k = 0; k < VPT; ++k)
+                    if (k == k_hit) oute[k] -= gEall;
             }
-            st_row_t<T, VPT, true>(ge_out + (size_t)i * S, j0, S, true, oute);
+            if (inside) st_row_t<T, VPT, true>(ge_out + (size_t)i * S, j0, S, true, oute);
         }
         side_sum = side_sum_next;
         side_prev_last = side_prev_next;
     }
 }
 
+template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED>
+int launch_mma_bwd_fast_impl(const MmaParams& prm, cudaStream_t stream) {
+    using L = FastLayout<THREADS * VPT, T, SOFT>;
+    auto kern = mma_bwd_fast_kernel<THREADS, VPT, T, SOFT, RAGGED>;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) {
+            cudaGetLastError();
+            return SIMULST_E_LAUNCH;
+        }
+        attr_set[dev & 63] = true;
+    }
+    kern<<<prm.N, THREADS, L::kTotal, stream>>>(prm);
+    return check_launch();
+}
+
+// returns 1 when the row does not qualify (the caller then uses the generic kernel)
 template <int THREADS, int VPT, typename T, bool SOFT>
 int launch_mma_bwd_fast(const MmaParams& prm, cudaStream_t stream) {
-    if constexpr (THREADS / kWarp > kFastMaxWarps || VPT % 8 != 0) {
+    constexpr int CAP = THREADS * VPT;
+    if constexpr (THREADS / kWarp > kFastMaxWarps || VPT % 4 != 0 || VPT > 12 ||
+                  FastLayout<CAP, T, SOFT>::kTotal > 227 * 1024) {
         return 1;
     } else {
-        constexpr int CAP = THREADS * VPT;
-        using L = FastLayout<CAP, T, SOFT>;
-        // dense rows only: no mask, the row fills the CTA, TMA staging and 16-byte rows legal
-        if (prm.mask != nullptr || prm.S != CAP || !prm.vec_out || !prm.tma) return 1;
-        auto kern = mma_bwd_fast_kernel<THREADS, VPT, T, SOFT>;
-        static bool attr_set[64] = {};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (!attr_set[dev & 63]) {
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) {
-                cudaGetLastError();
-                return SIMULST_E_LAUNCH;
-            }
-            attr_set[dev & 63] = true;
-        }
-        kern<<<prm.N, THREADS, L::kTotal, stream>>>(prm);
-        return check_launch();
+        // unmasked rows, TMA staging and 16-byte rows legal, every thread wholly inside or
+        // outside the row
+        if (prm.mask != nullptr || !prm.vec_out || !prm.tma) return 1;
+        if (prm.S > CAP || prm.S % VPT != 0) return 1;
+        return prm.S == CAP ? launch_mma_bwd_fast_impl<THREADS, VPT, T, SOFT, false>(prm, stream)
+                            : launch_mma_bwd_fast_impl<THREADS, VPT, T, SOFT, true>(prm, stream);
     }
 }
 

@@ -192,14 +192,17 @@ def test_pipelined_and_generic_kernels_agree(masked, soft):
         torch.testing.assert_close(a, b, rtol=5e-6, atol=5e-6 * scale)
 
 
-@pytest.mark.parametrize("shape", [(3, 17, 1024), (5, 9, 256), (4, 6, 512), (2, 5, 2048)])
+@pytest.mark.parametrize("shape", [(3, 17, 1024), (5, 9, 256), (4, 6, 512), (2, 5, 2048), (2, 4, 4096), (2, 4, 6144),
+                                   (3, 6, 1000), (2, 5, 1504), (2, 4, 6000), (2, 5, 264)])
 @pytest.mark.parametrize("soft", [False, True])
 @pytest.mark.parametrize("mp", [False, True])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_fast_backward_matches_generic(shape, soft, mp, dtype):
     """The dense fast-path backward (mma_bwd_fast.cuh) performs the generic kernel's arithmetic
     in the same order: bit-identical without mass preservation; with it, the correction
-    ok*g'_last is formed from block totals (one rounding apart), so results agree to a few ulp."""
+    ok*g'_last is formed from block totals (one rounding apart), so results agree to a few ulp.
+    Shapes: rows that fill the CTA (4..16 warps, 8 and 12 elements per thread) and ragged rows
+    (S a multiple of the per-thread element count, tails neutralised in shared memory)."""
     from simulst_b200 import _lib
     lib = _lib.load()
     n, t, s_len = shape
