@@ -27,7 +27,7 @@ int INST_NAME(const MmaParams& prm, int mode, int threads, int vpt, cudaStream_t
                                              : launch_mma_bwd_fast<TH, VP, InstT, true>(prm, stream); \
             if (rc != 1) return rc;             /* 1 = row does not qualify for the dense fast path */ \
         }                                                                                 \
-        if constexpr (TH <= kPipeMaxThreads) {                                            \
+        if constexpr (TH <= 256) {      /* the pipelined backward is validated up to 8 warps */ \
             if (prm.tma && prm.pipe && mode != kModeSoftCk) {                             \
                 const int rc = mode == kModeHard ? launch_mma_bwd_pipe<TH, VP, InstT, false>(prm, stream) \
                                                  : launch_mma_bwd_pipe<TH, VP, InstT, true>(prm, stream); \

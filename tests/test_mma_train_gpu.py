@@ -169,14 +169,15 @@ def test_tma_and_cooperative_staging_agree():
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("shape", [(3, 17, 1024), (3, 7, 1000), (2, 5, 1504), (2, 3, 6000), (2, 5, 264), (2, 4, 4096)])
 @pytest.mark.parametrize("masked", [False, True])
 @pytest.mark.parametrize("soft", [False, True])
-def test_pipelined_and_generic_kernels_agree(masked, soft):
+def test_pipelined_and_generic_kernels_agree(masked, soft, shape):
     """The software-pipelined kernels and the generic (one scan per barrier) kernels evaluate the
     same formulas with different scan groupings: results agree to a few ulp of the row scale."""
     from simulst_b200 import _lib
     lib = _lib.load()
-    p, se, mask, ga, gb = _seeded(3, 17, 1024, seed=11, masked=masked)
+    p, se, mask, ga, gb = _seeded(*shape, seed=11, masked=masked)
     outs = []
     try:
         for pipe in (3, 0):
@@ -188,7 +189,9 @@ def test_pipelined_and_generic_kernels_agree(masked, soft):
         if a is None:
             assert b is None
             continue
-        scale = float(b.abs().max())
+        # rounding differences live at the scale of the incoming gradients (suffix sums of
+        # gradient-sized terms that largely cancel), not at the scale of the result
+        scale = max(float(b.abs().max()), float(ga.abs().max()), float(gb.abs().max()) if soft else 0.0)
         torch.testing.assert_close(a, b, rtol=5e-6, atol=5e-6 * scale)
 
 
