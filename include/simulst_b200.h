@@ -129,6 +129,41 @@ int simulst_mma_train_bwd(const void* p_choose, int p_dtype,
                           void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * MMA training path with the expected-delay epilogue.  Same as
+ * simulst_mma_train_fwd / _bwd plus
+ *   expected_delays       [N,T] f32 out   sum_j (j+1) * alpha'_ij  of the OUTPUT (mass-preserved)
+ *                                          row: the first step of the latency loss,
+ *                                          codebase/criterion/mma_criterion.py:146-157
+ *                                          (`steps * alpha_all` summed over the source axis),
+ *                                          a by-product of the row scan instead of a second
+ *                                          pass over alpha.  NULL: not produced.
+ *   grad_expected_delays  [N,T] f32 in    dL/d expected_delays; the backward kernel adds
+ *                                          gd_i * (j+1) to dL/d alpha'_ij on the fly, so a
+ *                                          criterion that touches alpha only through the delays
+ *                                          passes grad_alpha = NULL and the 4 B/element
+ *                                          grad_alpha read disappears.  NULL: no such term.
+ * Everything downstream of the delays (DifferentiableAverageLagging, head gathering, variance)
+ * works on [N,T] tensors and stays in the caller. */
+int simulst_mma_train_fwd_delays(const void* p_choose, int p_dtype,
+                                 const void* soft_energy, int e_dtype,
+                                 const uint8_t* padding_mask,
+                                 float* alpha, float* beta, float* side,
+                                 float* expected_delays,
+                                 int N, int T, int S,
+                                 float eps, int chunk_size, unsigned flags,
+                                 unsigned* status, void* stream);
+int simulst_mma_train_bwd_delays(const void* p_choose, int p_dtype,
+                                 const void* soft_energy, int e_dtype,
+                                 const uint8_t* padding_mask,
+                                 const float* alpha, const float* side,
+                                 const float* grad_alpha, const float* grad_beta,
+                                 const float* grad_expected_delays,
+                                 void* grad_p, int gp_dtype, void* grad_energy, int ge_dtype,
+                                 int N, int T, int S,
+                                 float eps, int chunk_size, unsigned flags,
+                                 void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Stand-alone pieces (same math, rows independent): used when the reference functions are
  * called one by one rather than through monotonic_attention_process_train.
  */

@@ -280,3 +280,15 @@ def mma_process_infer(
     else:
         beta = alpha.view(n, 1, s_len)
     return new_step.view(n), head_read.view(n), alpha, beta
+
+
+def expected_delays(alpha):
+    """Step 2 of MMACriterion.compute_latency_loss (reference
+    codebase/criterion/mma_criterion.py:146-157): `steps = arange(1, 1+src_len)` broadcast over
+    alpha, `expected_delays = sum(steps * alpha, dim=-1)`.  The criterion module itself needs
+    fairseq to import, so this three-line expression is restated, not loaded (parity unpinned by
+    reference fixtures, like the rest of the latency loss -- SURVEY 8c)."""
+    import torch
+    src_len = alpha.size(-1)
+    steps = torch.arange(1, 1 + src_len).unsqueeze(0).unsqueeze(1).expand_as(alpha).type_as(alpha)
+    return torch.sum(steps * alpha, dim=-1)

@@ -45,6 +45,14 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_int, c_void_p, c_int,
                                       c_int, c_int, c_int, c_float, c_int, c_uint, c_void_p]),
+    "simulst_mma_train_fwd_delays": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_int, c_int, c_int, c_float, c_int, c_uint,
+                                             c_void_p, c_void_p]),
+    "simulst_mma_train_bwd_delays": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_int, c_void_p, c_int,
+                                             c_int, c_int, c_int, c_float, c_int, c_uint, c_void_p]),
     "simulst_soft_attention_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                            c_int, c_int, c_int, c_float, c_int, c_uint,
                                            c_void_p, c_void_p]),

@@ -80,6 +80,15 @@ int simulst_mma_train_fwd(const void* p_choose, int p_dtype, const void* soft_en
                           const uint8_t* padding_mask, float* alpha, float* beta, float* side,
                           int N, int T, int S, float eps, int chunk_size, unsigned flags,
                           unsigned* status, void* stream) {
+    return simulst_mma_train_fwd_delays(p_choose, p_dtype, soft_energy, e_dtype, padding_mask, alpha, beta, side,
+                                        nullptr, N, T, S, eps, chunk_size, flags, status, stream);
+}
+
+int simulst_mma_train_fwd_delays(const void* p_choose, int p_dtype, const void* soft_energy, int e_dtype,
+                                 const uint8_t* padding_mask, float* alpha, float* beta, float* side,
+                                 float* expected_delays,
+                                 int N, int T, int S, float eps, int chunk_size, unsigned flags,
+                                 unsigned* status, void* stream) {
     const bool soft = (flags & SIMULST_MMA_SOFT) != 0u;
     if (p_choose == nullptr || alpha == nullptr || !valid_dtype(p_dtype)) return SIMULST_E_ARG;
     if (soft && (soft_energy == nullptr || beta == nullptr || e_dtype != p_dtype)) return SIMULST_E_ARG;
@@ -96,6 +105,7 @@ int simulst_mma_train_fwd(const void* p_choose, int p_dtype, const void* soft_en
     MmaParams prm{};
     prm.p = p_choose; prm.e = soft ? soft_energy : nullptr; prm.mask = padding_mask;
     prm.alpha = alpha; prm.beta = soft ? beta : nullptr; prm.side = side;
+    prm.delays = expected_delays;
     prm.N = N; prm.T = T; prm.S = S; prm.eps = eps; prm.chunk = chunk_size; prm.flags = flags;
     prm.status = status;
     prm.tma = g_use_tma && ((size_t)S * esz) % 16 == 0 && aligned(p_choose, 16) &&
@@ -119,6 +129,18 @@ int simulst_mma_train_bwd(const void* p_choose, int p_dtype, const void* soft_en
                           void* grad_p, int gp_dtype, void* grad_energy, int ge_dtype,
                           int N, int T, int S, float eps, int chunk_size, unsigned flags,
                           void* stream) {
+    return simulst_mma_train_bwd_delays(p_choose, p_dtype, soft_energy, e_dtype, padding_mask, alpha, side,
+                                        grad_alpha, grad_beta, nullptr, grad_p, gp_dtype, grad_energy, ge_dtype,
+                                        N, T, S, eps, chunk_size, flags, stream);
+}
+
+int simulst_mma_train_bwd_delays(const void* p_choose, int p_dtype, const void* soft_energy, int e_dtype,
+                                 const uint8_t* padding_mask, const float* alpha, const float* side,
+                                 const float* grad_alpha, const float* grad_beta,
+                                 const float* grad_expected_delays,
+                                 void* grad_p, int gp_dtype, void* grad_energy, int ge_dtype,
+                                 int N, int T, int S, float eps, int chunk_size, unsigned flags,
+                                 void* stream) {
     const bool soft = (flags & SIMULST_MMA_SOFT) != 0u;
     const bool mp = (flags & SIMULST_MMA_MASS_PRESERVATION) != 0u;
     if (p_choose == nullptr || alpha == nullptr || grad_p == nullptr || !valid_dtype(p_dtype)) return SIMULST_E_ARG;
@@ -139,6 +161,7 @@ int simulst_mma_train_bwd(const void* p_choose, int p_dtype, const void* soft_en
     prm.p = p_choose; prm.e = soft ? soft_energy : nullptr; prm.mask = padding_mask;
     prm.alpha = const_cast<float*>(alpha); prm.side = const_cast<float*>(side);
     prm.g_alpha = grad_alpha; prm.g_beta = soft ? grad_beta : nullptr;
+    prm.g_delays = grad_expected_delays;
     prm.g_p = grad_p; prm.g_e = soft ? grad_energy : nullptr;
     prm.N = N; prm.T = T; prm.S = S; prm.eps = eps; prm.chunk = chunk_size; prm.flags = flags;
     prm.status = nullptr;

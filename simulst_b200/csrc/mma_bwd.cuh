@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : 1)) mma_
     const int NS = plan.n_stage;
     const bool has_ga = prm.g_alpha != nullptr;
     const bool has_gb = SOFT && prm.g_beta != nullptr;
+    const bool has_gd = prm.g_delays != nullptr;    // gradient of the expected delays: g'_ij += gd_i * (j+1)
 
     const size_t row0 = (size_t)n * T_len * S;
     const T* gp_in = reinterpret_cast<const T*>(prm.p) + row0;
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : 1)) mma_
             side_sum = side[2 * i + 1];
             if (i > 0) side_prev_last = side[2 * (i - 1)];
         }
+        const float gd = has_gd ? prm.g_delays[(size_t)n * T_len + i] : 0.f;
         if (prm.tma) mbar_wait(&bars[s], parity);
 
         float p[VPT], E[VPT], am1[VPT], gA[VPT], gB[VPT];
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : 1)) mma_
             const bool in = is_in(k);
             if (!in) am1[k] = 0.f;
             if (!has_ga || !in) gA[k] = 0.f;
+            if (has_gd && in) gA[k] = __fmaf_rn((float)(j0 + k + 1), gd, gA[k]);
             if (!has_gb || !in) gB[k] = 0.f;
             a_save[k] = am1[k];
             // undo mass preservation on the stored row: the recurrence ran on the raw alpha

@@ -361,7 +361,9 @@ struct FastLayout {
 // (p = 0, energy = -inf, alpha = grads = 0) -- the bulk copies only ever write [0, S) -- so the
 // step loop needs no per-element bounds checks: outside threads compute on neutral data, their
 // e-term is zeroed by one multiply, and they skip the stores.
-template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED>
+// DELAYS: the gradient of the expected delays is compiled in (dense rows: separate instantiation;
+// ragged rows: always compiled in, run-time flag).
+template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED, bool DELAYS>
 __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS * VPT <= 2048 ? 2 : 1)))
 mma_bwd_fast_kernel(const MmaParams prm) {
     constexpr int NW = THREADS / kWarp;
@@ -392,6 +394,7 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     const bool mp = (prm.flags & SIMULST_MMA_MASS_PRESERVATION) != 0u;
     const bool has_ga = prm.g_alpha != nullptr;
     const bool has_gb = SOFT && prm.g_beta != nullptr;
+    const bool has_gd = DELAYS && prm.g_delays != nullptr;        // gradient of the expected delays: g'_ij += gd_i * (j+1)
     const bool inside = !RAGGED || j0 < S;              // this thread's VPT columns exist
     const bool mp_last = mp && j0 + VPT == S;           // owner of the column mass preservation rewrites
 
@@ -483,6 +486,14 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         side_sum = side[2 * (T_len - 1) + 1];
         if (T_len > 1) side_prev_last = side[2 * (T_len - 2)];
     }
+    const float* gd_row = nullptr;
+    float gd_cur = 0.f;
+    if constexpr (DELAYS) {
+        if (has_gd) {
+            gd_row = prm.g_delays + (size_t)n * T_len + opaque_zero;
+            gd_cur = gd_row[T_len - 1];
+        }
+    }
 
     // row max of the first step's energies (every later one is reduced one iteration ahead)
     float m_cur = 0.f, Emax_cur = -INFINITY;
@@ -501,6 +512,10 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     for (int qi = 0; qi < T_len; ++qi) {
         const int i = T_len - 1 - qi;
         if (qi + NS - 1 < T_len) issue(qi + NS - 1);
+        float gd_next = 0.f;
+        if constexpr (DELAYS) {
+            if (has_gd && i > 0) gd_next = ldg_opaque(gd_row + i - 1);
+        }
         float side_sum_next = 0.f, side_prev_next = 0.f;
         if (mp && i > 0) {
             side_sum_next = ldg_opaque(side + 2 * (i - 1) + 1);
@@ -711,6 +726,13 @@ mma_bwd_fast_kernel(const MmaParams prm) {
 #pragma unroll
             for (int q = 0; q < H; ++q) gA[q] = f2(0.f);
         }
+        if constexpr (DELAYS) if (has_gd) {
+            const float2 gd2 = f2(gd_cur), fj = f2((float)j0);
+#pragma unroll
+            for (int q = 0; q < H; ++q)
+                gA[q] = fma2(add2(fj, f2((float)(2 * q + 1), (float)(2 * q + 2))), gd2, gA[q]);
+            if (mp) gA_last = __fmaf_rn((float)S, gd_cur, gA_last);
+        }
         float okg = 0.f;
         if (mp) {
             const float ok = (side_sum >= 0.0f && side_sum <= 1.0f) ? 1.0f : 0.0f;
@@ -854,13 +876,14 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         }
         side_sum = side_sum_next;
         side_prev_last = side_prev_next;
+        if constexpr (DELAYS) gd_cur = gd_next;
     }
 }
 
-template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED>
+template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED, bool DELAYS>
 int launch_mma_bwd_fast_impl(const MmaParams& prm, cudaStream_t stream) {
     using L = FastLayout<THREADS * VPT, T, SOFT>;
-    auto kern = mma_bwd_fast_kernel<THREADS, VPT, T, SOFT, RAGGED>;
+    auto kern = mma_bwd_fast_kernel<THREADS, VPT, T, SOFT, RAGGED, DELAYS>;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -887,8 +910,9 @@ int launch_mma_bwd_fast(const MmaParams& prm, cudaStream_t stream) {
         // outside the row
         if (prm.mask != nullptr || !prm.vec_out || !prm.tma) return 1;
         if (prm.S > CAP || prm.S % VPT != 0) return 1;
-        return prm.S == CAP ? launch_mma_bwd_fast_impl<THREADS, VPT, T, SOFT, false>(prm, stream)
-                            : launch_mma_bwd_fast_impl<THREADS, VPT, T, SOFT, true>(prm, stream);
+        if (prm.S != CAP) return launch_mma_bwd_fast_impl<THREADS, VPT, T, SOFT, true, true>(prm, stream);
+        return prm.g_delays != nullptr ? launch_mma_bwd_fast_impl<THREADS, VPT, T, SOFT, false, true>(prm, stream)
+                                       : launch_mma_bwd_fast_impl<THREADS, VPT, T, SOFT, false, false>(prm, stream);
     }
 }
 

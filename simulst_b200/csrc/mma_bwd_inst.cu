@@ -28,7 +28,7 @@ int INST_NAME(const MmaParams& prm, int mode, int threads, int vpt, cudaStream_t
             if (rc != 1) return rc;             /* 1 = row does not qualify for the dense fast path */ \
         }                                                                                 \
         if constexpr (TH <= 256) {      /* the pipelined backward is validated up to 8 warps */ \
-            if (prm.tma && prm.pipe && mode != kModeSoftCk) {                             \
+            if (prm.tma && prm.pipe && mode != kModeSoftCk && prm.g_delays == nullptr) {                             \
                 const int rc = mode == kModeHard ? launch_mma_bwd_pipe<TH, VP, InstT, false>(prm, stream) \
                                                  : launch_mma_bwd_pipe<TH, VP, InstT, true>(prm, stream); \
                 if (rc != 1) return rc;         /* 1 = row too long for the pipelined kernel */ \

@@ -24,6 +24,8 @@ struct MmaParams {
     const float* g_beta;    // bwd
     void* g_p;              // bwd out
     void* g_e;              // bwd out
+    float* delays;          // fwd: optional [N,T] expected delays sum_j (j+1)*alpha'_ij
+    const float* g_delays;  // bwd: optional [N,T] gradient w.r.t. the expected delays
     int N, T, S;
     float eps;
     int chunk;

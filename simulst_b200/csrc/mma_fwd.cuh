@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(THREADS) mma_fwd_kernel(const MmaParams prm, c
     const int j0 = tid * VPT;
     const float eps = prm.eps;
     const bool mp = (prm.flags & SIMULST_MMA_MASS_PRESERVATION) != 0u;
+    const bool want_d = prm.delays != nullptr;
     const float fill = (prm.flags & SIMULST_MMA_ENERGY_F16_FILL) ? -1e4f : -1e8f;
     const bool vec_out = FULL || prm.vec_out != 0;
 
@@ -249,14 +250,16 @@ __global__ void __launch_bounds__(THREADS) mma_fwd_kernel(const MmaParams prm, c
         nan_out = nan_out || (utot != utot);     // NaN anywhere in u poisons the thread total
 
         // ---------------- mass preservation + soft attention
-        if (mp || SOFT) {
+        if (mp || SOFT || want_d) {
             float rsum = 0.f;           // row sum entering the residual
+            float wloc = 0.f;           // sum of (j+1)*alpha over this thread's columns (expected delay)
             float rloc[VPT];            // r_j, then local inclusive suffix sums
             float a_last = 0.f;
 #pragma unroll
             for (int k = 0; k < VPT; ++k) {
                 const bool is_last = at_last(k);
                 if (is_last) a_last = a[k];
+                if (want_d) wloc = __fmaf_rn(a[k], (float)(j0 + k + 1), wloc);
                 const bool counted = mp_add || !is_last;
                 if (mp && counted) rsum += a[k];
                 if (SOFT) rloc[k] = ((mp && !counted) || !is_in(k)) ? 0.f : a[k] * rD[k];
@@ -277,11 +280,28 @@ __global__ void __launch_bounds__(THREADS) mma_fwd_kernel(const MmaParams prm, c
                 const float ws = warp_sum(rsum);
                 if (lane == 0) xc.slot(1)[warp] = ws;
             }
+            if (want_d) {
+                const float wd = warp_sum(wloc);
+                if (lane == 0) xc.slot(2)[warp] = wd;
+            }
             __syncthreads();
             float resid = 0.f, row_total = 0.f;
             if (mp) {
                 row_total = combine_sum<NW>(xc.slot(1), lane);
                 resid = 1.0f - fminf(fmaxf(row_total, 0.0f), 1.0f);
+            }
+            if (want_d) {
+                // expected delay of the OUTPUT row (mma_criterion.py:146-157): the raw weighted
+                // sum corrected for the column mass preservation rewrites (owner thread knows it)
+                const float wtot = combine_sum<NW>(xc.slot(2), lane);
+                float* dst = prm.delays + (size_t)n * T_len + i;
+                if (!mp) {
+                    if (tid == 0) *dst = wtot;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < VPT; ++k)
+                        if (at_last(k)) *dst = wtot + (float)(last + 1) * (mp_add ? resid : (resid - a_last));
+                }
             }
             float R[VPT];
             if (SOFT && !CHUNK) {

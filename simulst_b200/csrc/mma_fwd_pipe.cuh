@@ -47,7 +47,9 @@ struct PipePlan {
     }
 };
 
-template <int THREADS, int VPT, typename T, bool SOFT, bool FULL>
+// DELAYS: the expected-delay epilogue is compiled in (dense rows: a separate instantiation, so
+// the plain kernel carries none of it; ragged / masked rows: always compiled in, run-time flag)
+template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS>
 __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS <= 256 ? 2 : 1)))
 mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
     constexpr int NW = THREADS / kWarp;
@@ -155,6 +157,8 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
     }
     float m_cur = 0.f;                      // row max of the step INV runs next
     float rt_prev = 0.f, rsum_prev = 0.f;   // thread totals (r-suffix, row sum) of the step RECR scans next
+    float wsum_prev = 0.f;                  // thread total of (j+1)*alpha (expected delay) of that step
+    const bool want_d = DELAYS && prm.delays != nullptr;
     float a_last_raw = 0.f;                 // owner thread: alpha at the mass-preservation column
     unsigned umax = 0u;                     // FULL rows: first-level prob_check
     bool bad = false;                       // ragged rows: exact per-element check
@@ -276,6 +280,10 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
             const float ws = warp_sum(rsum_prev);
             if (lane == 0) xw[5 * kXStride + warp] = ws;
         }
+        if (want_d) {
+            const float wd = warp_sum(wsum_prev);
+            if (lane == 0) xw[6 * kXStride + warp] = wd;
+        }
 
         __syncthreads();                    // ================================ the barrier
         // every thread has read ring slot `slotI`: refill it with the row NS steps ahead
@@ -314,6 +322,13 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
                 }
                 st_row2_f32<VPT, FULL>(g_beta + (size_t)i * S, j0, S, vec_out, b);
             }
+            if (want_d) {
+                // expected delay (mma_criterion.py:146-157): the weighted row sum left out the
+                // column mass preservation rewrites (or holds its raw value when the residual is
+                // ADDED), so the residual enters with that column's weight
+                const float wtot = xw_sum<NW>(xw + 6 * kXStride, lane);
+                if (tid == 0) prm.delays[(size_t)n * T_len + i] = mp ? wtot + (float)(last + 1) * resid : wtot;
+            }
             if (own_last) {
                 // the row itself was stored one iteration ago; patch the one column
                 g_alpha[(size_t)i * S + last] = mp_add ? (a_last_raw + resid) : resid;
@@ -329,7 +344,7 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
 #pragma unroll
             for (int q = 0; q < H; ++q) a_prev[q] = min2(z[q], 1.0f);      // z >= 0: P >= 0, s >= 0
             st_row2_f32<VPT, FULL>(g_alpha + (size_t)it * S, j0, S, vec_out, a_prev);
-            if (mp || SOFT) {
+            if (mp || SOFT || want_d) {
                 // alpha entering the row sum / the soft-attention numerator: the mass-preservation
                 // column is left out when it is REPLACED (its residual is added analytically)
                 float2 a_s[H];
@@ -349,6 +364,13 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
 #pragma unroll
                     for (int q = 1; q < H; ++q) acc = add2(acc, a_s[q]);
                     rsum_prev = acc.x + acc.y;
+                }
+                if (want_d) {
+                    const float2 fj = f2((float)j0);
+                    float2 acc = mul2(a_s[0], add2(fj, f2(1.0f, 2.0f)));
+#pragma unroll
+                    for (int q = 1; q < H; ++q) acc = fma2(a_s[q], add2(fj, f2((float)(2 * q + 1), (float)(2 * q + 2))), acc);
+                    wsum_prev = acc.x + acc.y;
                 }
             }
         }
@@ -399,7 +421,7 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
 
 // ------------------------------------------------------------------ host-side launcher
 // Returns 1 when the row does not fit the pipelined kernel (caller falls back to the generic one).
-template <int THREADS, int VPT, typename T, bool SOFT, bool FULL>
+template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS>
 int launch_mma_fwd_pipe_impl(const MmaParams& prm, cudaStream_t stream) {
     PipePlan plan;
     plan.rows = SOFT ? 2 : 1;
@@ -410,7 +432,7 @@ int launch_mma_fwd_pipe_impl(const MmaParams& prm, cudaStream_t stream) {
     const size_t budget = THREADS <= 128 ? 56 * 1024 : (THREADS <= 256 ? 110 * 1024 : 220 * 1024);
     while (plan.n_stage > 1 && plan.total() > budget) --plan.n_stage;
     if (plan.total() > budget || (SOFT && plan.n_stage < 2)) return 1;
-    auto kern = mma_fwd_pipe_kernel<THREADS, VPT, T, SOFT, FULL>;
+    auto kern = mma_fwd_pipe_kernel<THREADS, VPT, T, SOFT, FULL, DELAYS>;
     static size_t attr_set[64] = {};    // per device: largest dynamic smem size opted into
     int dev = 0;
     cudaGetDevice(&dev);
@@ -429,8 +451,9 @@ int launch_mma_fwd_pipe_impl(const MmaParams& prm, cudaStream_t stream) {
 template <int THREADS, int VPT, typename T, bool SOFT>
 int launch_mma_fwd_pipe(const MmaParams& prm, cudaStream_t stream) {
     const bool full = prm.mask == nullptr && prm.S == THREADS * VPT && prm.vec_out;
-    return full ? launch_mma_fwd_pipe_impl<THREADS, VPT, T, SOFT, true>(prm, stream)
-                : launch_mma_fwd_pipe_impl<THREADS, VPT, T, SOFT, false>(prm, stream);
+    if (!full) return launch_mma_fwd_pipe_impl<THREADS, VPT, T, SOFT, false, true>(prm, stream);
+    return prm.delays != nullptr ? launch_mma_fwd_pipe_impl<THREADS, VPT, T, SOFT, true, true>(prm, stream)
+                                 : launch_mma_fwd_pipe_impl<THREADS, VPT, T, SOFT, true, false>(prm, stream);
 }
 
 }  // namespace simulst

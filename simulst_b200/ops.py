@@ -31,7 +31,7 @@ class MMATrainFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, p_choose: Tensor, soft_energy: Optional[Tensor], padding_mask: Optional[Tensor],
                 eps: float, mass_preservation: bool, chunk_size: Optional[int],
-                left_padding: bool = False):
+                left_padding: bool = False, with_delays: bool = False):
         lib = _lib.load()
         dev = _lib.require_cuda(p_choose, soft_energy, padding_mask)
         if p_choose.dim() != 3:
@@ -61,49 +61,51 @@ class MMATrainFunction(torch.autograd.Function):
         alpha = torch.empty((n, t, s), dtype=torch.float32, device=dev)
         beta = torch.empty((n, t, s), dtype=torch.float32, device=dev) if soft else None
         side = torch.empty((n, t, 2), dtype=torch.float32, device=dev) if mass_preservation else None
+        delays = torch.empty((n, t), dtype=torch.float32, device=dev) if with_delays else None
         status = _lib.status_word(dev)
         chunk = int(chunk_size) if chunk_size else 0
         with torch.cuda.device(dev):
-            rc = lib.simulst_mma_train_fwd(
+            rc = lib.simulst_mma_train_fwd_delays(
                 _lib.ptr(p), _lib.dtype_enum(p.dtype), _lib.ptr(e),
                 _lib.dtype_enum(e.dtype) if soft else 0, _lib.ptr(mask),
-                _lib.ptr(alpha), _lib.ptr(beta), _lib.ptr(side),
+                _lib.ptr(alpha), _lib.ptr(beta), _lib.ptr(side), _lib.ptr(delays),
                 n, t, s, float(eps), chunk, flags, _lib.ptr(status), _lib.stream_ptr(dev))
-        _lib.check(rc, "simulst_mma_train_fwd")
+        _lib.check(rc, "simulst_mma_train_fwd_delays")
         _lib.maybe_check(dev)
         ctx.save_for_backward(p, e, mask, alpha, side)
         ctx.cfg = (n, t, s, float(eps), chunk, flags, soft)
         ctx.in_dtypes = (p_choose.dtype, soft_energy.dtype if soft else None)
         ctx.mark_non_differentiable()
-        if soft:
-            return alpha, beta
-        return alpha, alpha.new_empty(0)
+        ctx.set_materialize_grads(False)        # an unused output costs no zero-filled gradient
+        return (alpha, beta if soft else alpha.new_empty(0),
+                delays if with_delays else alpha.new_empty(0))
 
     @staticmethod
-    def backward(ctx, g_alpha, g_beta):
+    def backward(ctx, g_alpha, g_beta, g_delays):
         lib = _lib.load()
         p, e, mask, alpha, side = ctx.saved_tensors
         n, t, s, eps, chunk, flags, soft = ctx.cfg
         dev = p.device
         ga = g_alpha.contiguous().float() if g_alpha is not None else None
         gb = g_beta.contiguous().float() if (soft and g_beta is not None) else None
+        gd = g_delays.contiguous().float() if (g_delays is not None and g_delays.numel() == n * t) else None
         grad_p = torch.empty_like(p)
         grad_e = torch.empty_like(e) if soft else None
         with torch.cuda.device(dev):
-            rc = lib.simulst_mma_train_bwd(
+            rc = lib.simulst_mma_train_bwd_delays(
                 _lib.ptr(p), _lib.dtype_enum(p.dtype), _lib.ptr(e),
                 _lib.dtype_enum(e.dtype) if soft else 0, _lib.ptr(mask),
-                _lib.ptr(alpha), _lib.ptr(side), _lib.ptr(ga), _lib.ptr(gb),
+                _lib.ptr(alpha), _lib.ptr(side), _lib.ptr(ga), _lib.ptr(gb), _lib.ptr(gd),
                 _lib.ptr(grad_p), _lib.dtype_enum(p.dtype), _lib.ptr(grad_e),
                 _lib.dtype_enum(e.dtype) if soft else 0,
                 n, t, s, eps, chunk, flags, _lib.stream_ptr(dev))
-        _lib.check(rc, "simulst_mma_train_bwd")
+        _lib.check(rc, "simulst_mma_train_bwd_delays")
         p_dt, e_dt = ctx.in_dtypes
         if grad_p.dtype != p_dt:
             grad_p = grad_p.to(p_dt)
         if soft and grad_e.dtype != e_dt:
             grad_e = grad_e.to(e_dt)
-        return grad_p, grad_e, None, None, None, None, None
+        return grad_p, grad_e, None, None, None, None, None, None
 
 
 def mma_train(p_choose: Tensor, soft_energy: Optional[Tensor] = None,
@@ -112,11 +114,28 @@ def mma_train(p_choose: Tensor, soft_energy: Optional[Tensor] = None,
               left_padding: bool = False):
     """Fused expected alignment (+ mass preservation) (+ expected soft attention).
     Returns (alpha [N,T,S] fp32, beta [N,T,S] fp32); beta is alpha for hard attention."""
-    alpha, beta = MMATrainFunction.apply(p_choose, soft_energy, padding_mask, eps,
-                                         mass_preservation, chunk_size, left_padding)
+    alpha, beta, _ = MMATrainFunction.apply(p_choose, soft_energy, padding_mask, eps,
+                                            mass_preservation, chunk_size, left_padding, False)
     if soft_energy is None:
         beta = alpha
     return alpha, beta
+
+
+def mma_train_with_delays(p_choose: Tensor, soft_energy: Optional[Tensor] = None,
+                          padding_mask: Optional[Tensor] = None, eps: float = 1e-6,
+                          mass_preservation: bool = True, chunk_size: Optional[int] = None,
+                          left_padding: bool = False):
+    """mma_train plus the expected delays `sum_j (j+1) * alpha[n,i,j]` ([N,T] fp32) of the
+    returned alpha: step 2 of MMACriterion.compute_latency_loss
+    (reference codebase/criterion/mma_criterion.py:146-157) as a by-product of the alignment
+    kernel.  Differentiable: a loss that reaches alpha only through the delays (and beta) makes
+    the backward kernel skip the [N,T,S] grad_alpha read entirely.
+    Returns (alpha, beta, expected_delays)."""
+    alpha, beta, delays = MMATrainFunction.apply(p_choose, soft_energy, padding_mask, eps,
+                                                 mass_preservation, chunk_size, left_padding, True)
+    if soft_energy is None:
+        beta = alpha
+    return alpha, beta, delays
 
 
 # ----------------------------------------------------------------------------- stand-alone MMA pieces
