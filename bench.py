@@ -317,7 +317,47 @@ def run_ours(args):
     extras = {}
     cpu_base = None
     if rank == 0 and world == 1:
-        extras = side_benchmarks(lib, dev)
+        # expected-delay epilogue on the same resident buffers: the latency
+        # loss reaches alpha only through the [N,T] delays, so the backward reads no grad_alpha
+        try:
+            delays = torch.empty(N_ROWS, T, device=dev)
+            g_del = torch.randn(N_ROWS, T, device=dev) / S
+
+            def step_delays():
+                rc = lib.simulst_mma_train_fwd_delays(p.data_ptr(), _lib.BF16, e.data_ptr(), _lib.BF16, None,
+                                                      alpha.data_ptr(), beta.data_ptr(), side.data_ptr(),
+                                                      delays.data_ptr(), N_ROWS, T, S, EPS, 0, flags,
+                                                      status.data_ptr(), st)
+                _lib.check(rc, "simulst_mma_train_fwd_delays")
+                rc = lib.simulst_mma_train_bwd_delays(p.data_ptr(), _lib.BF16, e.data_ptr(), _lib.BF16, None,
+                                                      alpha.data_ptr(), side.data_ptr(), None, gb.data_ptr(),
+                                                      g_del.data_ptr(), gp.data_ptr(), _lib.BF16, ge.data_ptr(),
+                                                      _lib.BF16, N_ROWS, T, S, EPS, 0, flags, st)
+                _lib.check(rc, "simulst_mma_train_bwd_delays")
+
+            for _ in range(3):
+                step_delays()
+            torch.cuda.synchronize()
+            d0 = torch.cuda.Event(enable_timing=True)
+            d1 = torch.cuda.Event(enable_timing=True)
+            d0.record(stream)
+            for _ in range(10):
+                step_delays()
+            d1.record(stream)
+            torch.cuda.synchronize()
+            d_ms = d0.elapsed_time(d1) / 10
+            peak_d, _ = measured_peak()
+            extras["latency_epilogue"] = {
+                "metric": "mma_fwd_bwd_with_expected_delays_elements_per_s", "value": elems / (d_ms * 1e-3),
+                "unit": UNIT, "ms_per_step": d_ms,
+                "algorithmic_bytes_per_element": BYTES_FWD + BYTES_BWD - 4,
+                "roofline_frac": elems * (BYTES_FWD + BYTES_BWD - 4) / (d_ms * 1e-3) / 1e9 / peak_d,
+                "note": "simulst_mma_train_fwd_delays + simulst_mma_train_bwd_delays(grad_alpha=NULL): "
+                        "expected delays as a by-product of the forward scan, their gradient injected in "
+                        "the backward kernel (mma_criterion.py:146-157)"}
+        except Exception as exc:  # pragma: no cover
+            extras["latency_epilogue"] = {"error": repr(exc)}
+        extras.update(side_benchmarks(lib, dev))
         best, mean, sec, cores = time_cpu(reps=2, warmup=1)
         cpu_base = {"value": mean, "unit": UNIT, "cores": cores, "kind": "port",
                     "sample": f"{CPU_SAMPLE_ROWS} of {N_ROWS} rows (full tgt {T} x src {S}), fp32, "

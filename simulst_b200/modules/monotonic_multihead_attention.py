@@ -20,7 +20,7 @@ import torch
 from torch import Tensor
 
 from .. import ops
-from ..utils.monotonic_attention import mma_process_train
+from ..utils.monotonic_attention import mma_process_train, mma_process_train_with_delays
 
 
 class B200MonotonicAttentionMixin:
@@ -47,16 +47,28 @@ class B200MonotonicAttentionMixin:
                 "soft",
                 key_padding_mask=None,
             )
-            alpha, beta = mma_process_train(
-                p_choose, soft_energy, key_padding_mask, eps=self.eps,
-                mass_preservation=self.mass_preservation, chunk_size=self.chunk_size)
+            alpha, beta, delays = self._alignment(p_choose, soft_energy, key_padding_mask, self.chunk_size)
         else:
-            alpha, beta = mma_process_train(
-                p_choose, None, key_padding_mask, eps=self.eps,
-                mass_preservation=self.mass_preservation)
+            alpha, beta, delays = self._alignment(p_choose, None, key_padding_mask, None)
             soft_energy = alpha
 
+        # [bsz*heads, tgt] expected delays of this layer (sum_j (j+1)*alpha) when the module has
+        # `with_expected_delays = True`: what MMACriterion.compute_latency_loss
+        # (mma_criterion.py:146-157) otherwise recomputes from alpha.  Kept on the module so a
+        # criterion can use it instead of re-reading alpha; the reference's return tuple is unchanged.
+        self.expected_delays = delays
+
         return p_choose, alpha, beta, soft_energy
+
+    def _alignment(self, p_choose, soft_energy, key_padding_mask, chunk_size):
+        if getattr(self, "with_expected_delays", False):
+            return mma_process_train_with_delays(
+                p_choose, soft_energy, key_padding_mask, eps=self.eps,
+                mass_preservation=self.mass_preservation, chunk_size=chunk_size)
+        alpha, beta = mma_process_train(
+            p_choose, soft_energy, key_padding_mask, eps=self.eps,
+            mass_preservation=self.mass_preservation, chunk_size=chunk_size)
+        return alpha, beta, None
 
     def monotonic_attention_process_infer(
         self,

@@ -57,3 +57,13 @@ def mma_process_train(p_choose: Tensor, soft_energy: Optional[Tensor],
     (expected alignment -> mass preservation -> expected soft attention)."""
     return ops.mma_train(p_choose, soft_energy, padding_mask, eps=eps,
                          mass_preservation=mass_preservation, chunk_size=chunk_size)
+
+
+def mma_process_train_with_delays(p_choose: Tensor, soft_energy: Optional[Tensor],
+                                  padding_mask: Optional[Tensor] = None, eps: float = 1e-6,
+                                  mass_preservation: bool = True, chunk_size: Optional[int] = None):
+    """mma_process_train plus the expected delays ``sum_j (j+1) * alpha[n,i,j]`` ([N,T]) that
+    MMACriterion.compute_latency_loss derives from alpha (reference
+    codebase/criterion/mma_criterion.py:146-157), produced by the same launch."""
+    return ops.mma_train_with_delays(p_choose, soft_energy, padding_mask, eps=eps,
+                                     mass_preservation=mass_preservation, chunk_size=chunk_size)

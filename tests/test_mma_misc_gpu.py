@@ -165,6 +165,11 @@ def test_module_mixin_train_and_infer_against_oracle():
     a_o, b_o = omma.mma_process_train(p, e, None, 1e-6, True, None)
     assert_parity(alpha.cpu(), a_o, "alpha")
     assert_parity(beta.cpu(), b_o, "beta")
+    assert host.expected_delays is None
+    host.with_expected_delays = True            # opt-in latency-loss epilogue (mma_criterion.py:146-157)
+    _, alpha_d, _, _ = host.monotonic_attention_process_train(q, k, None)
+    assert torch.equal(alpha_d, alpha)
+    assert_parity(host.expected_delays.cpu(), omma.expected_delays(a_o), "expected_delays")
     host2 = Host(p[:, :1].to(DEV), e[:, :1].to(DEV))
     _, alpha1, beta1 = host2.monotonic_attention_process_infer(q[:1], k, None, {})
     ns, hr, a1, b1 = omma.mma_process_infer(p[:, 0], torch.zeros(bsz * 2, dtype=torch.long), e[:, :1], None, True)
