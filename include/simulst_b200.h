@@ -83,6 +83,9 @@ int simulst_mma_set_pipeline(int mode);
 /* 1 = CIF forward/backward through the TMA-staged tile kernels when rows are 16-byte aligned
  * and C <= 512 (default), 0 = always the per-warp kernels (same results bit for bit) */
 int simulst_cif_set_tile(int enable);
+/* Tuning override for the CIF tile kernels: frames staged per forward chunk and frames per
+ * backward tile (multiple of 8); 0 = automatic (48 KB / 32 KB of shared memory).  Returns 0 or E_ARG. */
+int simulst_cif_set_tile_rows(int fwd_chunk_frames, int bwd_tile_frames);
 
 /* ---------------------------------------------------------------------------------------
  * MMA training path, forward.   Replaces, fused in one launch,

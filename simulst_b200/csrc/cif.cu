@@ -478,8 +478,17 @@ using namespace simulst;
 
 // development / test switch: route simulst_cif_fwd/_bwd through the per-warp fallback kernels
 static int g_cif_force_fallback = 0;
+// tuning overrides (0 = automatic): frames per forward tile chunk, frames per backward tile
+static int g_cif_fc = 0, g_cif_fr = 0;
 
 extern "C" {
+
+int simulst_cif_set_tile_rows(int fwd_chunk_frames, int bwd_tile_frames) {
+    if (fwd_chunk_frames < 0 || bwd_tile_frames < 0 || bwd_tile_frames % kTileWarps != 0) return SIMULST_E_ARG;
+    g_cif_fc = fwd_chunk_frames;
+    g_cif_fr = bwd_tile_frames;
+    return SIMULST_OK;
+}
 
 int simulst_cif_set_tile(int enable) {
     g_cif_force_fallback = enable ? 0 : 1;
@@ -536,7 +545,7 @@ int simulst_cif_fwd(const void* input, int x_dtype, const float* csum, const flo
                 constexpr int NP = decltype(np)::value;
                 if (tile) {
                     const size_t row_bytes = (size_t)C * sizeof(TX);
-                    const int FC = (int)std::max<size_t>(8, 48 * 1024 / row_bytes);
+                    const int FC = g_cif_fc > 0 ? g_cif_fc : (int)std::max<size_t>(8, 48 * 1024 / row_bytes);
                     const size_t smem = kTileHeader + (size_t)FC * row_bytes;
                     auto kern = cif_fwd_tile_kernel<TX, TA, NP>;
                     if (int rc = set_smem(kern, smem)) return rc;
@@ -586,6 +595,7 @@ int simulst_cif_bwd(const void* input, int x_dtype, const float* csum, const flo
                     const size_t row_bytes = (size_t)C * sizeof(TX);
                     int FR = (int)(32 * 1024 / row_bytes) / kTileWarps * kTileWarps;
                     FR = std::max(kTileWarps, std::min(64, FR));
+                    if (g_cif_fr > 0) FR = g_cif_fr;
                     const int GR = FR / 2 + 2;
                     const size_t smem = kTileHeader + (size_t)(FR + GR) * row_bytes;
                     auto kern = cif_bwd_tile_kernel<TX, TA, NP>;

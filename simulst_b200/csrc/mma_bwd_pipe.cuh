@@ -689,9 +689,13 @@ int launch_mma_bwd_pipe_impl(const MmaParams& prm, cudaStream_t stream) {
 
 template <int THREADS, int VPT, typename T, bool SOFT>
 int launch_mma_bwd_pipe(const MmaParams& prm, cudaStream_t stream) {
+    // Dense rows that fill the CTA only.  The ragged / masked instantiation computes on the
+    // unwritten tails of its shared-memory rings before masking them out, which is only safe
+    // when those bytes happen to hold finite values (found with -inf tails left behind by another
+    // kernel); such rows go to the generic kernel (return 1).
     const bool full = prm.mask == nullptr && prm.S == THREADS * VPT && prm.vec_out;
-    return full ? launch_mma_bwd_pipe_impl<THREADS, VPT, T, SOFT, true>(prm, stream)
-                : launch_mma_bwd_pipe_impl<THREADS, VPT, T, SOFT, false>(prm, stream);
+    if (!full) return 1;
+    return launch_mma_bwd_pipe_impl<THREADS, VPT, T, SOFT, true>(prm, stream);
 }
 
 }  // namespace simulst

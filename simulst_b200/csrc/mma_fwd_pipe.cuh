@@ -49,7 +49,10 @@ struct PipePlan {
 
 // DELAYS: the expected-delay epilogue is compiled in (dense rows: a separate instantiation, so
 // the plain kernel carries none of it; ragged / masked rows: always compiled in, run-time flag)
-template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS>
+// RAGGED (with FULL): S < THREADS*VPT, S a multiple of VPT -- threads are wholly inside or wholly
+// outside the row; outside threads initialise the ring tails to neutral values once (p = 0,
+// energy = -inf; the bulk copies only write [0, S)), compute without bounds checks, skip stores.
+template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS, bool RAGGED = false>
 __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS <= 256 ? 2 : 1)))
 mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
     constexpr int NW = THREADS / kWarp;
@@ -104,6 +107,19 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
         for (int s = 0; s < NS; ++s) mbar_init(&bars[s], kIssuers);
         mbar_fence_init();
     }
+    const bool inside = !RAGGED || j0 < S;
+    if (RAGGED && !inside) {
+        const T ninf = from_f32<T>(-INFINITY), zero = from_f32<T>(0.f);
+        for (int s = 0; s < NS; ++s) {
+            T* sp = reinterpret_cast<T*>(stage0 + (size_t)(s * plan.rows) * plan.row_bytes);
+            T* se = reinterpret_cast<T*>(stage0 + (size_t)(s * plan.rows + 1) * plan.row_bytes);
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) {
+                sp[j0 + k] = zero;
+                if (SOFT) se[j0 + k] = ninf;
+            }
+        }
+    }
     if (mp_add) {
         const float cnt = warp_sum((float)n_live);
         if (lane == 0) xbuf[warp] = cnt;
@@ -116,7 +132,7 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
     // element of this thread that sits on the mass-preservation column (-1: none)
     int k_last = -1;
     if (FULL) {
-        if (tid == THREADS - 1) k_last = VPT - 1;
+        if (RAGGED ? (j0 + VPT == S) : (tid == THREADS - 1)) k_last = VPT - 1;
     } else if (last >= j0 && last < j0 + VPT) {
         k_last = last - j0;
     }
@@ -320,7 +336,7 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
                     for (int k = 0; k < VPT; ++k)
                         if (!is_live(k)) SIMULST_EL(b, k) = 0.f;
                 }
-                st_row2_f32<VPT, FULL>(g_beta + (size_t)i * S, j0, S, vec_out, b);
+                if (inside) st_row2_f32<VPT, FULL>(g_beta + (size_t)i * S, j0, S, vec_out, b);
             }
             if (want_d) {
                 // expected delay (mma_criterion.py:146-157): the weighted row sum left out the
@@ -343,7 +359,7 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
             finish_u_prefix<VPT>(ubase, sl, P, sfull, z);
 #pragma unroll
             for (int q = 0; q < H; ++q) a_prev[q] = min2(z[q], 1.0f);      // z >= 0: P >= 0, s >= 0
-            st_row2_f32<VPT, FULL>(g_alpha + (size_t)it * S, j0, S, vec_out, a_prev);
+            if (inside) st_row2_f32<VPT, FULL>(g_alpha + (size_t)it * S, j0, S, vec_out, a_prev);
             if (mp || SOFT || want_d) {
                 // alpha entering the row sum / the soft-attention numerator: the mass-preservation
                 // column is left out when it is REPLACED (its residual is added analytically)
@@ -421,7 +437,7 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
 
 // ------------------------------------------------------------------ host-side launcher
 // Returns 1 when the row does not fit the pipelined kernel (caller falls back to the generic one).
-template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS>
+template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS, bool RAGGED = false>
 int launch_mma_fwd_pipe_impl(const MmaParams& prm, cudaStream_t stream) {
     PipePlan plan;
     plan.rows = SOFT ? 2 : 1;
@@ -432,7 +448,7 @@ int launch_mma_fwd_pipe_impl(const MmaParams& prm, cudaStream_t stream) {
     const size_t budget = THREADS <= 128 ? 56 * 1024 : (THREADS <= 256 ? 110 * 1024 : 220 * 1024);
     while (plan.n_stage > 1 && plan.total() > budget) --plan.n_stage;
     if (plan.total() > budget || (SOFT && plan.n_stage < 2)) return 1;
-    auto kern = mma_fwd_pipe_kernel<THREADS, VPT, T, SOFT, FULL, DELAYS>;
+    auto kern = mma_fwd_pipe_kernel<THREADS, VPT, T, SOFT, FULL, DELAYS, RAGGED>;
     static size_t attr_set[64] = {};    // per device: largest dynamic smem size opted into
     int dev = 0;
     cudaGetDevice(&dev);
@@ -450,7 +466,11 @@ int launch_mma_fwd_pipe_impl(const MmaParams& prm, cudaStream_t stream) {
 // SOFT here means infinite lookback; requires prm.tma (16-byte aligned rows).
 template <int THREADS, int VPT, typename T, bool SOFT>
 int launch_mma_fwd_pipe(const MmaParams& prm, cudaStream_t stream) {
-    const bool full = prm.mask == nullptr && prm.S == THREADS * VPT && prm.vec_out;
+    const bool dense = prm.mask == nullptr && prm.vec_out;
+    const bool full = dense && prm.S == THREADS * VPT;
+    // ragged dense rows: every thread wholly inside or wholly outside the row
+    if (dense && !full && prm.S % VPT == 0 && prm.S < THREADS * VPT)
+        return launch_mma_fwd_pipe_impl<THREADS, VPT, T, SOFT, true, true, true>(prm, stream);
     if (!full) return launch_mma_fwd_pipe_impl<THREADS, VPT, T, SOFT, false, true>(prm, stream);
     return prm.delays != nullptr ? launch_mma_fwd_pipe_impl<THREADS, VPT, T, SOFT, true, true>(prm, stream)
                                  : launch_mma_fwd_pipe_impl<THREADS, VPT, T, SOFT, true, false>(prm, stream);

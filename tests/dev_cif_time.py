@@ -55,8 +55,17 @@ def timeit(fn, reps=7):
         ts.append(e0.elapsed_time(e1) * 1e3)
     return sorted(ts)[len(ts) // 2]
 
+import os
+if os.environ.get("TILE"):
+    fc, fr = [int(v) for v in os.environ["TILE"].split(",")]
+    assert lib.simulst_cif_set_tile_rows(fc, fr) == 0
 es = x.element_size()
 plan(); fwd(); bwd(); torch.cuda.synchronize()
+# back-to-back chain (what bench.py times): plan + fwd + bwd, no flush in between
+def chain():
+    plan(); fwd(); return bwd()
+tc = timeit(chain)
+print(f"TILE={os.environ.get('TILE','auto')} chain {tc:.1f} us", flush=True)
 tp, tf, tb = timeit(plan), timeit(fwd), timeit(bwd)
 bf = B * S * C * es + B * T * C * es + B * S * 8 + B * T * es
 bb = 2 * B * S * C * es + B * T * C * es + B * S * 8
