@@ -196,7 +196,8 @@ def test_pipelined_and_generic_kernels_agree(masked, soft, shape):
 
 
 @pytest.mark.parametrize("shape", [(3, 17, 1024), (5, 9, 256), (4, 6, 512), (2, 5, 2048), (2, 4, 4096), (2, 4, 6144),
-                                   (3, 6, 1000), (2, 5, 1504), (2, 4, 6000), (2, 5, 264)])
+                                   (3, 6, 1000), (2, 5, 1504), (2, 4, 6000), (2, 5, 264),
+                                   (2, 1, 1024), (3, 2, 512), (2, 1, 6000), (150, 3, 256)])
 @pytest.mark.parametrize("soft", [False, True])
 @pytest.mark.parametrize("mp", [False, True])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
