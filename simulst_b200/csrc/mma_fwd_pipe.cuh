@@ -47,6 +47,28 @@ struct PipePlan {
     }
 };
 
+// Compile-time shared-memory plan of one configuration (same arithmetic as PipePlan): ring
+// depth, row pitch and stash size are constants in the kernel, so ring-slot addresses cost no
+// run-time multiplies.
+template <int THREADS, int VPT, typename T, bool SOFT>
+struct PipeStatic {
+    static constexpr int kRows = SOFT ? 2 : 1;
+    static constexpr int kRowBytes = ((THREADS * VPT * (int)sizeof(T)) + 127) / 128 * 128;
+    static constexpr int kStashBytes = SOFT ? kExStash * THREADS * VPT * 4 : 0;
+    static constexpr int kHeader = 128 + 2 * kPipeSlots * kXStride * 4 + 128;
+    // keep 4 CTAs of a 128-thread configuration resident (<= 56 KB each); long rows: what fits
+    static constexpr size_t kBudget = THREADS <= 128 ? 56 * 1024 : (THREADS <= 256 ? 110 * 1024 : 220 * 1024);
+    static constexpr size_t total(int ns) { return (size_t)kHeader + (size_t)ns * kRows * kRowBytes + (size_t)kStashBytes; }
+    static constexpr int pick() {
+        int ns = kPipeStages;
+        while (ns > 1 && total(ns) > kBudget) --ns;
+        return ns;
+    }
+    static constexpr int kNS = pick();
+    static constexpr bool kFits = total(kNS) <= kBudget && (!SOFT || kNS >= 2);
+    static constexpr size_t kTotal = total(kNS);
+};
+
 // DELAYS: the expected-delay epilogue is compiled in (dense rows: a separate instantiation, so
 // the plain kernel carries none of it; ragged / masked rows: always compiled in, run-time flag)
 // RAGGED (with FULL): S < THREADS*VPT, S a multiple of VPT -- threads are wholly inside or wholly
@@ -54,7 +76,8 @@ struct PipePlan {
 // energy = -inf; the bulk copies only write [0, S)), compute without bounds checks, skip stores.
 template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS, bool RAGGED = false>
 __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS <= 256 ? 2 : 1)))
-mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
+mma_fwd_pipe_kernel(const MmaParams prm) {
+    using PS = PipeStatic<THREADS, VPT, T, SOFT>;
     constexpr int NW = THREADS / kWarp;
     constexpr int kIssuers = (SOFT && NW > 1) ? 2 : 1;     // warps that issue TMA copies
     constexpr int H = VPT / 2;
@@ -64,8 +87,8 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     float* xbuf = reinterpret_cast<float*>(smem + 128);               // [2][kPipeSlots][32]
     float* bcast = xbuf + 2 * kPipeSlots * kXStride;                  // [4] 1/D at the mass-preservation column
-    unsigned char* stage0 = smem + plan.header_bytes();
-    float4* stash = reinterpret_cast<float4*>(stage0 + (size_t)plan.n_stage * plan.rows * plan.row_bytes);
+    unsigned char* stage0 = smem + PS::kHeader;
+    float4* stash = reinterpret_cast<float4*>(stage0 + PS::kNS * PS::kRows * PS::kRowBytes);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(kFull, tid >> 5, 0)   /* shuffle: known warp-uniform */;
     const int n = blockIdx.x;
@@ -75,7 +98,7 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
     const bool mp = (prm.flags & SIMULST_MMA_MASS_PRESERVATION) != 0u;
     const float fill = (prm.flags & SIMULST_MMA_ENERGY_F16_FILL) ? -1e4f : -1e8f;
     const bool vec_out = FULL || prm.vec_out != 0;
-    const int NS = plan.n_stage;
+    constexpr int NS = PS::kNS;
 
     const T* gp = reinterpret_cast<const T*>(prm.p) + (size_t)n * T_len * S;
     const T* ge = SOFT ? reinterpret_cast<const T*>(prm.e) + (size_t)n * T_len * S : nullptr;
@@ -111,8 +134,8 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
     if (RAGGED && !inside) {
         const T ninf = from_f32<T>(-INFINITY), zero = from_f32<T>(0.f);
         for (int s = 0; s < NS; ++s) {
-            T* sp = reinterpret_cast<T*>(stage0 + (size_t)(s * plan.rows) * plan.row_bytes);
-            T* se = reinterpret_cast<T*>(stage0 + (size_t)(s * plan.rows + 1) * plan.row_bytes);
+            T* sp = reinterpret_cast<T*>(stage0 + (s * PS::kRows) * PS::kRowBytes);
+            T* se = reinterpret_cast<T*>(stage0 + (s * PS::kRows + 1) * PS::kRowBytes);
 #pragma unroll
             for (int k = 0; k < VPT; ++k) {
                 sp[j0 + k] = zero;
@@ -141,8 +164,8 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
 
     // ---- row staging ring
     const unsigned row_bytes = (unsigned)(S * sizeof(T));
-    auto stage_p = [&](int s) { return reinterpret_cast<T*>(stage0 + (size_t)(s * plan.rows) * plan.row_bytes); };
-    auto stage_e = [&](int s) { return reinterpret_cast<T*>(stage0 + (size_t)(s * plan.rows + 1) * plan.row_bytes); };
+    auto stage_p = [&](int s) { return reinterpret_cast<T*>(stage0 + (s * PS::kRows) * PS::kRowBytes); };
+    auto stage_e = [&](int s) { return reinterpret_cast<T*>(stage0 + (s * PS::kRows + 1) * PS::kRowBytes); };
     // one elected lane of warp 0 copies the p row, one of warp 1 (if there is one) the energy
     // row; each arrives on the slot's barrier with its own byte count (warp-uniform branches)
     auto issue = [&](int i, int s) {
@@ -439,27 +462,20 @@ mma_fwd_pipe_kernel(const MmaParams prm, const PipePlan plan) {
 // Returns 1 when the row does not fit the pipelined kernel (caller falls back to the generic one).
 template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS, bool RAGGED = false>
 int launch_mma_fwd_pipe_impl(const MmaParams& prm, cudaStream_t stream) {
-    PipePlan plan;
-    plan.rows = SOFT ? 2 : 1;
-    plan.row_bytes = ((THREADS * VPT * (int)sizeof(T)) + 127) / 128 * 128;
-    plan.stash_bytes = SOFT ? kExStash * THREADS * VPT * 4 : 0;
-    plan.n_stage = kPipeStages;
-    // keep 4 CTAs of a 128-thread configuration resident (<= 56 KB each); long rows: what fits
-    const size_t budget = THREADS <= 128 ? 56 * 1024 : (THREADS <= 256 ? 110 * 1024 : 220 * 1024);
-    while (plan.n_stage > 1 && plan.total() > budget) --plan.n_stage;
-    if (plan.total() > budget || (SOFT && plan.n_stage < 2)) return 1;
+    using PS = PipeStatic<THREADS, VPT, T, SOFT>;
+    if (!PS::kFits) return 1;
     auto kern = mma_fwd_pipe_kernel<THREADS, VPT, T, SOFT, FULL, DELAYS, RAGGED>;
     static size_t attr_set[64] = {};    // per device: largest dynamic smem size opted into
     int dev = 0;
     cudaGetDevice(&dev);
-    if (plan.total() > attr_set[dev & 63]) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total()) != cudaSuccess) {
+    if (PS::kTotal > attr_set[dev & 63]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS::kTotal) != cudaSuccess) {
             cudaGetLastError();
             return SIMULST_E_LAUNCH;
         }
-        attr_set[dev & 63] = plan.total();
+        attr_set[dev & 63] = PS::kTotal;
     }
-    kern<<<prm.N, THREADS, plan.total(), stream>>>(prm, plan);
+    kern<<<prm.N, THREADS, PS::kTotal, stream>>>(prm);
     return check_launch();
 }
 
