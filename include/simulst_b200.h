@@ -57,6 +57,10 @@ extern "C" {
                                             instead of -1e8 (monotonic_attention.py:106) */
 #define SIMULST_MMA_LEFT_PADDING 8u      /* mass_preservation(left_padding=True)         */
 
+#define SIMULST_MMA_RIGHT_PADDING 16u    /* caller's promise: padding_mask[n,j] = (j >= len_n), i.e.
+                                            right padding (what mass_preservation(left_padding=False)
+                                            and MMACriterion assume); lets masked rows take the dense
+                                            backward kernel instead of the arbitrary-mask one */
 #define SIMULST_MMA_MAX_SRC 16384        /* longest source row a single CTA keeps on chip */
 
 int simulst_version(void);

@@ -22,6 +22,7 @@ MMA_MASS_PRESERVATION = 1
 MMA_SOFT = 2
 MMA_ENERGY_F16_FILL = 4
 MMA_LEFT_PADDING = 8
+MMA_RIGHT_PADDING = 16
 MMA_MAX_SRC = 16384
 
 _lib = None
@@ -176,6 +177,24 @@ def set_strict(flag: bool):
 
 def is_strict() -> bool:
     return _strict
+
+
+_right_padding = os.environ.get("SIMULST_B200_RIGHT_PADDING", "0") not in ("0", "", "false", "False")
+
+
+def assume_right_padding(flag: bool):
+    """Promise that every padding mask handed to the MMA training op is a RIGHT-padding mask
+    (mask[n, j] == (j >= len_n)) -- what the reference's mass_preservation(left_padding=False) and
+    MMACriterion ("Only right padding is supported", mma_criterion.py:166) assume anyway.  Masked
+    rows then run the dense backward kernel (about 2x faster than the arbitrary-mask kernel at the
+    training shape).  Default off: without the promise arbitrary masks are honoured element by
+    element.  Env: SIMULST_B200_RIGHT_PADDING=1."""
+    global _right_padding
+    _right_padding = bool(flag)
+
+
+def right_padding_assumed() -> bool:
+    return _right_padding
 
 
 def status_word(device):

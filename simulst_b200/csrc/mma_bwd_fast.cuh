@@ -363,7 +363,12 @@ struct FastLayout {
 // e-term is zeroed by one multiply, and they skip the stores.
 // DELAYS: the gradient of the expected delays is compiled in (dense rows: separate instantiation;
 // ragged rows: always compiled in, run-time flag).
-template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED, bool DELAYS>
+// MASKED (with RAGGED): padding_mask is a RIGHT-padding mask (the caller's promise, flag
+// SIMULST_MMA_RIGHT_PADDING): row n is live on [0, L_n).  Columns >= L_n are neutralised after
+// each load (p = 0, energy = -inf, grads = 0) -- by one thread-uniform test everywhere except in
+// the single thread the boundary falls into -- their gradients are stored as zeros, and mass
+// preservation follows the reference's right-padding rule (residual ADDED at L_n - 1).
+template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED, bool DELAYS, bool MASKED = false>
 __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS * VPT <= 2048 ? 2 : 1)))
 mma_bwd_fast_kernel(const MmaParams prm) {
     constexpr int NW = THREADS / kWarp;
@@ -395,8 +400,7 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     const bool has_ga = prm.g_alpha != nullptr;
     const bool has_gb = SOFT && prm.g_beta != nullptr;
     const bool has_gd = DELAYS && prm.g_delays != nullptr;        // gradient of the expected delays: g'_ij += gd_i * (j+1)
-    const bool inside = !RAGGED || j0 < S;              // this thread's VPT columns exist
-    const bool mp_last = mp && j0 + VPT == S;           // owner of the column mass preservation rewrites
+    const bool in_row = !RAGGED || j0 < S;              // this thread's VPT columns exist
 
     const size_t row0 = (size_t)n * T_len * S;
     T* gp_out = reinterpret_cast<T*>(prm.g_p) + row0;
@@ -409,15 +413,22 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     const float* side = mp ? prm.side + (size_t)n * T_len * 2 + opaque_zero : nullptr;
 
     const WarpWeights<NW> ww(warp);
-    // weight of a column in the mass-preservation Jacobian: 0 for the rewritten column
-    const float w_lastcol = mp_last ? 0.0f : 1.0f;
-
     constexpr int kIssuers = NW < 5 ? NW : 5;
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) mbar_init(&bars[s], kIssuers);
         mbar_fence_init();
     }
-    if (RAGGED && !inside) {
+    int live_cnt = 0;
+    if (MASKED && in_row) {
+        const uint8_t* mrow = prm.mask + (size_t)n * S + j0;
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) live_cnt += (mrow[k] == 0) ? 1 : 0;
+    }
+    if (MASKED) {
+        live_cnt = __reduce_add_sync(kFull, live_cnt);
+        if (lane == 0) reinterpret_cast<int*>(xs(2, 3))[warp] = live_cnt;
+    }
+    if (RAGGED && !in_row) {
         // neutral tails (never overwritten by the bulk copies)
         const T ninf = from_f32<T>(-INFINITY), zero = from_f32<T>(0.f);
         for (int st_i = 0; st_i < NS; ++st_i) {
@@ -435,6 +446,23 @@ mma_bwd_fast_kernel(const MmaParams prm) {
             for (int k = 0; k < VPT; ++k) reinterpret_cast<float*>(alpha0 + a_i * L::kFRow)[j0 + k] = 0.f;
     }
     __syncthreads();
+    // live length of the row and this thread's share of it
+    int row_len = S;
+    if (MASKED) {
+        const int* ci = reinterpret_cast<const int*>(xs(2, 3));
+        row_len = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) row_len += ci[w];
+    }
+    const int nl = MASKED ? max(0, min(VPT, row_len - j0)) : VPT;      // live columns of this thread
+    const bool inside = MASKED ? nl > 0 : in_row;
+    const int last_col = MASKED ? max(row_len - 1, 0) : S - 1;
+    // owner of the mass-preservation column: dense rows REPLACE column S-1 (the last element of
+    // its thread); right-padded rows ADD the residual at L-1 (any element of its thread)
+    const bool mp_last = mp && !MASKED && j0 + VPT == S;
+    const int k_add = (MASKED && mp && row_len > 0 && last_col >= j0 && last_col < j0 + VPT) ? last_col - j0 : -1;
+    // weight of a column in the mass-preservation Jacobian: 0 for the REPLACED column
+    const float w_lastcol = mp_last ? 0.0f : 1.0f;
 
     const unsigned t_bytes = (unsigned)(S * sizeof(T)), f_bytes = (unsigned)(S * 4);
     // Producers: iteration q stages step i = T-1-q into stage q % 3 and alpha slot q % 4
@@ -475,6 +503,25 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     const float2 eps2 = f2(eps);
     const float in_f = inside ? 1.0f : 0.0f;
     (void)in_f;
+    // masked rows: neutralise the columns >= nl of a freshly loaded pair array
+    auto mask_tail = [&](float2 (&v)[H], float fill) {
+        if (MASKED && nl < VPT) {
+#pragma unroll
+            for (int k = 0; k < VPT; ++k)
+                if (k >= nl) SIMULST_EL(v, k) = fill;
+        }
+    };
+    // max over this thread's live columns of a staged energy row
+    auto row_max = [&](const void* row) -> float {
+        if (!MASKED || nl == VPT) return lds_row_max<T, VPT>(row, j0);
+        float2 v[H];
+        lds_row2<T, VPT>(row, j0, v);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < VPT; ++k)
+            if (k < nl) mx = fmaxf(mx, SIMULST_EL(v, k));
+        return mx;
+    };
     float2 carry[H];
 #pragma unroll
     for (int q = 0; q < H; ++q) carry[q] = f2(0.f);
@@ -499,7 +546,7 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     float m_cur = 0.f, Emax_cur = -INFINITY;
     if (SOFT) {
         mbar_wait(&bars[0], 0u);
-        Emax_cur = lds_row_max<T, VPT>(stage0 + L::kOffE, j0);
+        Emax_cur = row_max(stage0 + L::kOffE);
         const float wm = warp_max(Emax_cur);
         if (lane == 0) xs(2, 2)[warp] = wm;
         __syncthreads();
@@ -531,6 +578,8 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         float2 p[H], E[H];
         lds_row2<T, VPT>(st + L::kOffP, j0, p);
         if (SOFT) lds_row2<T, VPT>(st + L::kOffE, j0, E);
+        mask_tail(p, 0.f);
+        if (SOFT) mask_tail(E, -INFINITY);
 
         // ================= X1: exclusive cumprod of (1-p)+eps ; D = eps + prefix(e) ; arg-max owner
         // (the row maximum m_cur of this step's energies was reduced during the previous
@@ -560,8 +609,9 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                 const float2 tt = mul2(add2(E[q], nm), l2e);
                 exm[q] = f2(ex2_approx(tt.x), ex2_approx(tt.y));
                 ex[q] = add2(exm[q], eps2);
-                if (RAGGED) ex[q] = mul2(ex[q], f2(in_f));       // no eps from columns beyond the row
+                if (RAGGED && !MASKED) ex[q] = mul2(ex[q], f2(in_f));       // no eps from columns beyond the row
             }
+            mask_tail(ex, 0.f);                                  // nor from padded columns
 #pragma unroll
             for (int q = 0; q < H; ++q) {
                 etot += ex[q].x; Dl[q].x = etot;
@@ -623,6 +673,11 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                     lds_row2<float, VPT>(a_prev_row, j0, am1);
                     // undo mass preservation on the stored row: the recurrence ran on the raw alpha
                     if (mp_last) am1[H - 1].y = side_prev_last;
+                    if (MASKED && k_add >= 0) {
+#pragma unroll
+                        for (int k = 0; k < VPT; ++k)
+                            if (k == k_add) SIMULST_EL(am1, k) = side_prev_last;
+                    }
                 } else {
 #pragma unroll
                     for (int q = 0; q < H; ++q) am1[q] = f2((j0 + 2 * q == 0) ? 1.0f : 0.0f, 0.0f);
@@ -687,6 +742,7 @@ mma_bwd_fast_kernel(const MmaParams prm) {
             float gtot = 0.f;
             if (has_gb) {
                 lds_row2<float, VPT>(st + L::kOffGB, j0, gB);
+                mask_tail(gB, 0.f);
             } else {
 #pragma unroll
                 for (int q = 0; q < H; ++q) gB[q] = f2(0.f);
@@ -721,7 +777,8 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         float gA_last = 0.f;
         if (has_ga) {
             lds_row2<float, VPT>(st + L::kOffGA, j0, gA);
-            if (mp) gA_last = reinterpret_cast<const float*>(st + L::kOffGA)[S - 1];
+            mask_tail(gA, 0.f);
+            if (mp) gA_last = reinterpret_cast<const float*>(st + L::kOffGA)[last_col];
         } else {
 #pragma unroll
             for (int q = 0; q < H; ++q) gA[q] = f2(0.f);
@@ -731,7 +788,8 @@ mma_bwd_fast_kernel(const MmaParams prm) {
 #pragma unroll
             for (int q = 0; q < H; ++q)
                 gA[q] = fma2(add2(fj, f2((float)(2 * q + 1), (float)(2 * q + 2))), gd2, gA[q]);
-            if (mp) gA_last = __fmaf_rn((float)S, gd_cur, gA_last);
+            if (mp) gA_last = __fmaf_rn((float)(last_col + 1), gd_cur, gA_last);
+            mask_tail(gA, 0.f);
         }
         float okg = 0.f;
         if (mp) {
@@ -816,7 +874,7 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         float Emax_next = -INFINITY;
         if (SOFT && i > 0) {
             mbar_wait(&bars[s], parity);
-            Emax_next = lds_row_max<T, VPT>(stage0 + s * L::kStage + L::kOffE, j0);
+            Emax_next = row_max(stage0 + s * L::kStage + L::kOffE);
         }
         float gAinc = gAtot, ws = gEsum, wmax = Emax_next;
         if (SOFT) {
@@ -860,7 +918,12 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                 const float2 o = fma2(mul2(gL, rx[q]), neg1, mul2(gPk[q], cp[q]));
                 outp[2 * q] = o.x; outp[2 * q + 1] = o.y;
             }
-            if (inside) st_row_t<T, VPT, true>(gp_out + (size_t)i * S, j0, S, true, outp);
+            if (MASKED && nl < VPT) {
+#pragma unroll
+                for (int k = 0; k < VPT; ++k)
+                    if (k >= nl) outp[k] = 0.f;
+            }
+            if (MASKED ? in_row : inside) st_row_t<T, VPT, true>(gp_out + (size_t)i * S, j0, S, true, outp);
         }
         if (SOFT) {
             float oute[VPT];
@@ -872,7 +935,12 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                 for (int k = 0; k < VPT; ++k)
                     if (k == k_hit) oute[k] -= gEall;
             }
-            if (inside) st_row_t<T, VPT, true>(ge_out + (size_t)i * S, j0, S, true, oute);
+            if (MASKED && nl < VPT) {
+#pragma unroll
+                for (int k = 0; k < VPT; ++k)
+                    if (k >= nl) oute[k] = 0.f;
+            }
+            if (MASKED ? in_row : inside) st_row_t<T, VPT, true>(ge_out + (size_t)i * S, j0, S, true, oute);
         }
         side_sum = side_sum_next;
         side_prev_last = side_prev_next;
@@ -880,10 +948,10 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     }
 }
 
-template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED, bool DELAYS>
+template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED, bool DELAYS, bool MASKED = false>
 int launch_mma_bwd_fast_impl(const MmaParams& prm, cudaStream_t stream) {
     using L = FastLayout<THREADS * VPT, T, SOFT>;
-    auto kern = mma_bwd_fast_kernel<THREADS, VPT, T, SOFT, RAGGED, DELAYS>;
+    auto kern = mma_bwd_fast_kernel<THREADS, VPT, T, SOFT, RAGGED, DELAYS, MASKED>;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -908,8 +976,13 @@ int launch_mma_bwd_fast(const MmaParams& prm, cudaStream_t stream) {
     } else {
         // unmasked rows, TMA staging and 16-byte rows legal, every thread wholly inside or
         // outside the row
-        if (prm.mask != nullptr || !prm.vec_out || !prm.tma) return 1;
+        if (!prm.vec_out || !prm.tma) return 1;
         if (prm.S > CAP || prm.S % VPT != 0) return 1;
+        if (prm.mask != nullptr) {
+            // masked rows: only when the caller promises a right-padding mask
+            if (!(prm.flags & SIMULST_MMA_RIGHT_PADDING) || (prm.flags & SIMULST_MMA_LEFT_PADDING)) return 1;
+            return launch_mma_bwd_fast_impl<THREADS, VPT, T, SOFT, true, true, true>(prm, stream);
+        }
         if (prm.S != CAP) return launch_mma_bwd_fast_impl<THREADS, VPT, T, SOFT, true, true>(prm, stream);
         return prm.g_delays != nullptr ? launch_mma_bwd_fast_impl<THREADS, VPT, T, SOFT, false, true>(prm, stream)
                                        : launch_mma_bwd_fast_impl<THREADS, VPT, T, SOFT, false, false>(prm, stream);

@@ -58,6 +58,8 @@ class MMATrainFunction(torch.autograd.Function):
         if left_padding:
             flags |= _lib.MMA_LEFT_PADDING
         mask = _mask_u8(padding_mask, n, s, dev)
+        if mask is not None and not left_padding and _lib.right_padding_assumed():
+            flags |= _lib.MMA_RIGHT_PADDING
         alpha = torch.empty((n, t, s), dtype=torch.float32, device=dev)
         beta = torch.empty((n, t, s), dtype=torch.float32, device=dev) if soft else None
         side = torch.empty((n, t, 2), dtype=torch.float32, device=dev) if mass_preservation else None

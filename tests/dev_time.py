@@ -21,13 +21,18 @@ gp = torch.empty_like(p); ge = torch.empty_like(e)
 status = torch.zeros(1, dtype=torch.int32, device=dev)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 st = torch.cuda.current_stream().cuda_stream
+mask = None
+if os.environ.get('MASK'):
+    lens = torch.randint(S // 2, S + 1, (N,), generator=g)
+    mask = (torch.arange(S)[None, :] >= lens[:, None]).to(dev).view(torch.uint8).contiguous()
+mp_ = mask.data_ptr() if mask is not None else None
 flags = int(os.environ.get('FLAGS', '3'))
 
 def fwd():
-    return lib.simulst_mma_train_fwd(p.data_ptr(), 1, e.data_ptr(), 1, None, alpha.data_ptr(), beta.data_ptr(),
+    return lib.simulst_mma_train_fwd(p.data_ptr(), 1, e.data_ptr(), 1, mp_, alpha.data_ptr(), beta.data_ptr(),
                                      side.data_ptr(), N, T, S, 1e-6, 0, flags, status.data_ptr(), st)
 def bwd():
-    return lib.simulst_mma_train_bwd(p.data_ptr(), 1, e.data_ptr(), 1, None, alpha.data_ptr(), side.data_ptr(),
+    return lib.simulst_mma_train_bwd(p.data_ptr(), 1, e.data_ptr(), 1, mp_, alpha.data_ptr(), side.data_ptr(),
                                      ga.data_ptr(), gb.data_ptr() if flags & 1 else None, gp.data_ptr(), 1, ge.data_ptr(), 1,
                                      N, T, S, 1e-6, 0, flags, st)
 

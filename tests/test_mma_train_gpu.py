@@ -299,3 +299,48 @@ def test_host_pipeline_matches_device_path(chunks, streams):
     assert torch.equal(gp_h, p_d.grad.cpu()) and torch.equal(ge_h, e_d.grad.cpu())
     with pytest.raises(ValueError):
         pipe.step(p, e_h, ga, gb, gp_h, ge_h)       # unpinned host tensor
+
+
+@pytest.mark.parametrize("shape", [(4, 9, 1024), (3, 7, 1000), (2, 5, 1504), (2, 4, 4096), (3, 6, 264), (2, 3, 6000)])
+@pytest.mark.parametrize("soft", [False, True])
+@pytest.mark.parametrize("mp", [False, True])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_right_padding_promise_matches_arbitrary_mask_kernel(shape, soft, mp, dtype):
+    """With simulst_b200.assume_right_padding(True) masked rows run the dense backward kernel
+    (per-row live length instead of per-element mask tests): same gradients as the arbitrary-mask
+    kernel on right-padded batches, zeros at padded columns, and parity with the oracle."""
+    import simulst_b200
+    from simulst_b200 import _lib
+    lib = _lib.load()
+    n, t, s_len = shape
+    p, se, mask, ga, gb = _seeded(n, t, s_len, seed=31, masked=True)
+    p, se = p.to(dtype), se.to(dtype)
+    outs = []
+    try:
+        for promise in (True, False):
+            simulst_b200.assume_right_padding(promise)
+            lib.simulst_mma_set_pipeline(DEFAULT_PIPELINE if promise else 0)
+            outs.append(_run(p, se if soft else None, mask, mp, 0, soft, ga, gb if soft else None, dtype=dtype))
+    finally:
+        simulst_b200.assume_right_padding(False)
+        lib.simulst_mma_set_pipeline(DEFAULT_PIPELINE)
+    scale = max(float(ga.abs().max()), float(gb.abs().max()) if soft else 0.0)
+    ulp = 2.0 ** -7 if dtype == torch.bfloat16 else 5e-6
+    for k, (a, b) in enumerate(zip(*outs)):
+        if a is None:
+            assert b is None
+            continue
+        if k >= 2:      # gradients: exactly zero where the mask is set
+            assert not bool(a[mask.unsqueeze(1).expand_as(a)].any()), f"output {k}: non-zero gradient at padded columns"
+        # 16-bit outputs: two roundings of slightly different fp32 values can land two steps apart
+        atol = (2e-5 if dtype == torch.bfloat16 else 2e-6) * max(scale, float(b.float().abs().max()))
+        torch.testing.assert_close(a.float(), b.float(), rtol=ulp, atol=atol)
+    if dtype == torch.float32:
+        p_o = p.clone().requires_grad_()
+        se_o = se.clone().requires_grad_() if soft else None
+        a_o, b_o = omma.mma_process_train(p_o, se_o, mask, 1e-6, mp, None)
+        loss = (a_o * ga).sum() + ((b_o * gb).sum() if soft else 0.0)
+        loss.backward()
+        assert_parity(outs[0][2], p_o.grad, "grad_p", extra_atol=2e-6 * scale)
+        if soft:
+            assert_parity(outs[0][3], se_o.grad, "grad_soft_energy", extra_atol=2e-6 * scale)
