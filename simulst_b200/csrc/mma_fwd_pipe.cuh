@@ -74,7 +74,12 @@ struct PipeStatic {
 // RAGGED (with FULL): S < THREADS*VPT, S a multiple of VPT -- threads are wholly inside or wholly
 // outside the row; outside threads initialise the ring tails to neutral values once (p = 0,
 // energy = -inf; the bulk copies only write [0, S)), compute without bounds checks, skip stores.
-template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS, bool RAGGED = false>
+// MASKED (with FULL and RAGGED): padding_mask is a RIGHT-padding mask (caller's promise,
+// SIMULST_MMA_RIGHT_PADDING): row n is live on [0, L_n); columns >= L_n are neutralised after
+// each load (p = 0, energy = -inf) by a test that is thread-uniform except in the one thread
+// the boundary falls into; alpha and beta come out zero there, and mass preservation ADDS its
+// residual at L_n - 1 (monotonic_attention.py:186-193).
+template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS, bool RAGGED = false, bool MASKED = false>
 __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS <= 256 ? 2 : 1)))
 mma_fwd_pipe_kernel(const MmaParams prm) {
     using PS = PipeStatic<THREADS, VPT, T, SOFT>;
@@ -123,7 +128,14 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
     auto is_live = [&](int k) -> bool { return FULL ? true : ((live_bits >> k) & 1u) != 0u; };
     // mass_preservation: no mask / left padding -> REPLACE column S-1 with the residual of the
     // other columns; right padding -> ADD the residual of all columns at src_len-1.
-    const bool mp_add = !FULL && prm.mask != nullptr && !(prm.flags & SIMULST_MMA_LEFT_PADDING);
+    if constexpr (FULL && MASKED) {
+        if (j0 < S) {
+            const uint8_t* mrow = prm.mask + (size_t)n * S + j0;
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) n_live += (mrow[k] == 0) ? 1 : 0;
+        }
+    }
+    const bool mp_add = (!FULL || MASKED) && prm.mask != nullptr && !(prm.flags & SIMULST_MMA_LEFT_PADDING);
     int last = S - 1;
 
     if (tid == 0) {
@@ -153,14 +165,17 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
         __syncthreads();
     }
     // element of this thread that sits on the mass-preservation column (-1: none)
+    // live columns of this thread (right-padded rows); VPT everywhere else
+    const int nl = MASKED ? max(0, min(VPT, last + 1 - j0)) : VPT;
+    (void)nl;
     int k_last = -1;
-    if (FULL) {
+    if (FULL && !MASKED) {
         if (RAGGED ? (j0 + VPT == S) : (tid == THREADS - 1)) k_last = VPT - 1;
     } else if (last >= j0 && last < j0 + VPT) {
         k_last = last - j0;
     }
     const bool own_last = mp && k_last >= 0;
-    auto at_last = [&](int k) -> bool { return (FULL ? k == VPT - 1 : true) && k == k_last; };
+    auto at_last = [&](int k) -> bool { return ((FULL && !MASKED) ? k == VPT - 1 : true) && k == k_last; };
 
     // ---- row staging ring
     const unsigned row_bytes = (unsigned)(S * sizeof(T));
@@ -228,7 +243,14 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
             unsigned parM = parI;
             if (slotM == NS) { slotM = 0; parM ^= 1u; }
             mbar_wait(&bars[slotM], parM);
-            if constexpr (FULL && sizeof(T) == 2 && VPT % 8 == 0) {
+            if (MASKED && nl < VPT) {
+                float2 Em[H];
+                unsigned dummy = 0u;
+                lds_row2<T, VPT, false>(stage_e(slotM) + j0, Em, dummy);
+#pragma unroll
+                for (int k = 0; k < VPT; ++k)
+                    if (k < nl) em = fmaxf(em, SIMULST_EL(Em, k));
+            } else if constexpr (FULL && sizeof(T) == 2 && VPT % 8 == 0) {
                 // packed 16-bit max, one conversion at the end
                 using T2 = typename std::conditional<std::is_same<T, __half>::value, __half2, __nv_bfloat162>::type;
                 const uint4* src = reinterpret_cast<const uint4*>(stage_e(slotM) + j0);
@@ -266,6 +288,14 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
             if (SOFT) {
                 unsigned dummy = 0u;
                 lds_row2<T, VPT, false>(stage_e(slotI) + j0, E_n, dummy);
+            }
+            if (MASKED && nl < VPT) {
+#pragma unroll
+                for (int k = 0; k < VPT; ++k)
+                    if (k >= nl) {
+                        SIMULST_EL(p_n, k) = 0.f;
+                        if (SOFT) SIMULST_EL(E_n, k) = -INFINITY;
+                    }
             }
             if constexpr (!FULL) {
 #pragma unroll
@@ -358,6 +388,11 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
 #pragma unroll
                     for (int k = 0; k < VPT; ++k)
                         if (!is_live(k)) SIMULST_EL(b, k) = 0.f;
+                }
+                if (MASKED && nl < VPT) {
+#pragma unroll
+                    for (int k = 0; k < VPT; ++k)
+                        if (k >= nl) SIMULST_EL(b, k) = 0.f;
                 }
                 if (inside) st_row2_f32<VPT, FULL>(g_beta + (size_t)i * S, j0, S, vec_out, b);
             }
@@ -460,11 +495,11 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
 
 // ------------------------------------------------------------------ host-side launcher
 // Returns 1 when the row does not fit the pipelined kernel (caller falls back to the generic one).
-template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS, bool RAGGED = false>
+template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS, bool RAGGED = false, bool MASKED = false>
 int launch_mma_fwd_pipe_impl(const MmaParams& prm, cudaStream_t stream) {
     using PS = PipeStatic<THREADS, VPT, T, SOFT>;
     if (!PS::kFits) return 1;
-    auto kern = mma_fwd_pipe_kernel<THREADS, VPT, T, SOFT, FULL, DELAYS, RAGGED>;
+    auto kern = mma_fwd_pipe_kernel<THREADS, VPT, T, SOFT, FULL, DELAYS, RAGGED, MASKED>;
     static size_t attr_set[64] = {};    // per device: largest dynamic smem size opted into
     int dev = 0;
     cudaGetDevice(&dev);
@@ -482,6 +517,10 @@ int launch_mma_fwd_pipe_impl(const MmaParams& prm, cudaStream_t stream) {
 // SOFT here means infinite lookback; requires prm.tma (16-byte aligned rows).
 template <int THREADS, int VPT, typename T, bool SOFT>
 int launch_mma_fwd_pipe(const MmaParams& prm, cudaStream_t stream) {
+    // right-padded rows (caller's promise): dense path with a per-row live length
+    if (prm.mask != nullptr && (prm.flags & SIMULST_MMA_RIGHT_PADDING) && !(prm.flags & SIMULST_MMA_LEFT_PADDING) &&
+        prm.vec_out && prm.S % VPT == 0 && prm.S <= THREADS * VPT)
+        return launch_mma_fwd_pipe_impl<THREADS, VPT, T, SOFT, true, true, true, true>(prm, stream);
     const bool dense = prm.mask == nullptr && prm.vec_out;
     const bool full = dense && prm.S == THREADS * VPT;
     // ragged dense rows: every thread wholly inside or wholly outside the row
