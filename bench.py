@@ -357,6 +357,40 @@ def run_ours(args):
                         "the backward kernel (mma_criterion.py:146-157)"}
         except Exception as exc:  # pragma: no cover
             extras["latency_epilogue"] = {"error": repr(exc)}
+        # right-padded batch (SURVEY 8d variant ii: lengths ~ U[S/2, S]) with and without the
+        # caller's right-padding promise (simulst_b200.assume_right_padding / SIMULST_MMA_RIGHT_PADDING)
+        try:
+            gm = torch.Generator().manual_seed(1236)
+            lens = torch.randint(S // 2, S + 1, (N_ROWS,), generator=gm)
+            mask = (torch.arange(S)[None, :] >= lens[:, None]).to(dev).view(torch.uint8).contiguous()
+            res = {}
+            for name, fl in (("arbitrary_mask_kernels", flags), ("right_padding_promise", flags | _lib.MMA_RIGHT_PADDING)):
+                def step_masked():
+                    rc = lib.simulst_mma_train_fwd(p.data_ptr(), _lib.BF16, e.data_ptr(), _lib.BF16, mask.data_ptr(),
+                                                   alpha.data_ptr(), beta.data_ptr(), side.data_ptr(),
+                                                   N_ROWS, T, S, EPS, 0, fl, status.data_ptr(), st)
+                    _lib.check(rc, "simulst_mma_train_fwd")
+                    rc = lib.simulst_mma_train_bwd(p.data_ptr(), _lib.BF16, e.data_ptr(), _lib.BF16, mask.data_ptr(),
+                                                   alpha.data_ptr(), side.data_ptr(), ga.data_ptr(), gb.data_ptr(),
+                                                   gp.data_ptr(), _lib.BF16, ge.data_ptr(), _lib.BF16,
+                                                   N_ROWS, T, S, EPS, 0, fl, st)
+                    _lib.check(rc, "simulst_mma_train_bwd")
+                for _ in range(3):
+                    step_masked()
+                torch.cuda.synchronize()
+                m0 = torch.cuda.Event(enable_timing=True)
+                m1 = torch.cuda.Event(enable_timing=True)
+                m0.record(stream)
+                for _ in range(10):
+                    step_masked()
+                m1.record(stream)
+                torch.cuda.synchronize()
+                res[name] = {"ms_per_step": m0.elapsed_time(m1) / 10,
+                             "value": elems / (m0.elapsed_time(m1) / 10 * 1e-3), "unit": UNIT}
+            extras["masked_batch"] = {"config": "training shape, right-padded source lengths ~ U[S/2, S] (seed 1236), "
+                                                "elements counted over the full [N,T,S] grid", **res}
+        except Exception as exc:  # pragma: no cover
+            extras["masked_batch"] = {"error": repr(exc)}
         extras.update(side_benchmarks(lib, dev))
         best, mean, sec, cores = time_cpu(reps=2, warmup=1)
         cpu_base = {"value": mean, "unit": UNIT, "cores": cores, "kind": "port",
