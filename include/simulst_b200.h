@@ -49,6 +49,8 @@ extern "C" {
 #define SIMULST_ST_NAN 1u         /* "Nan in a probability tensor."                    */
 #define SIMULST_ST_RANGE 2u       /* "Incorrect values in a probability tensor"        */
 #define SIMULST_ST_NEGPROD 4u     /* safe_cumprod: input + eps < 0                     */
+#define SIMULST_ST_NOT_RIGHT_PADDED 8u /* SIMULST_MMA_RIGHT_PADDING was promised but a row's mask is not of
+                                          the form (j >= len): results of that call are invalid */
 
 /* flags of the MMA entry points */
 #define SIMULST_MMA_MASS_PRESERVATION 1u /* apply mass_preservation to the alpha output  */

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libsimulst_b200.so")
 F32, BF16, F16 = 0, 1, 2
 _DTYPE_ENUM = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
-ST_NAN, ST_RANGE, ST_NEGPROD = 1, 2, 4
+ST_NAN, ST_RANGE, ST_NEGPROD, ST_NOT_RIGHT_PADDED = 1, 2, 4, 8
 
 MMA_MASS_PRESERVATION = 1
 MMA_SOFT = 2
@@ -214,6 +214,9 @@ def raise_for_status(bits: int):
     if bits & ST_NEGPROD:
         raise RuntimeError("Safe cumprod can only take non-negative tensors as input."
                            "Consider use torch.cumprod if you want to calculate negative values.")
+    if bits & ST_NOT_RIGHT_PADDED:
+        raise RuntimeError("simulst_b200.assume_right_padding(True) is set but a padding mask was not a "
+                           "right-padding mask; the results of that call are invalid")
 
 
 def check_status(device=None):

@@ -168,6 +168,16 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
     // live columns of this thread (right-padded rows); VPT everywhere else
     const int nl = MASKED ? max(0, min(VPT, last + 1 - j0)) : VPT;
     (void)nl;
+    if constexpr (FULL && MASKED) {
+        // the promise is checked, not trusted: a mask that is not (j >= len) flags the status word
+        if (j0 < S && prm.status != nullptr) {
+            const uint8_t* mrow = prm.mask + (size_t)n * S + j0;
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) ok = ok && ((mrow[k] == 0) == (k < nl));
+            if (!ok) atomicOr(prm.status, SIMULST_ST_NOT_RIGHT_PADDED);
+        }
+    }
     int k_last = -1;
     if (FULL && !MASKED) {
         if (RAGGED ? (j0 + VPT == S) : (tid == THREADS - 1)) k_last = VPT - 1;

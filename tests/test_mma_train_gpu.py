@@ -344,3 +344,22 @@ def test_right_padding_promise_matches_arbitrary_mask_kernel(shape, soft, mp, dt
         assert_parity(outs[0][2], p_o.grad, "grad_p", extra_atol=2e-6 * scale)
         if soft:
             assert_parity(outs[0][3], se_o.grad, "grad_soft_energy", extra_atol=2e-6 * scale)
+
+
+def test_broken_right_padding_promise_is_reported():
+    """The promise is verified by the forward kernel: a mask with a hole raises at the next status check."""
+    import simulst_b200
+    from simulst_b200 import ops
+    dev = torch.device("cuda")
+    p, se, mask, _, _ = _seeded(3, 4, 512, seed=41, masked=True)
+    mask[1, 5] = True          # a padded column in the middle of row 1
+    mask[1, -1] = False
+    simulst_b200.check_status(dev)
+    try:
+        simulst_b200.assume_right_padding(True)
+        ops.mma_train(p.to(dev), se.to(dev), mask.to(dev))
+        with pytest.raises(RuntimeError, match="right-padding"):
+            simulst_b200.check_status(dev)
+        simulst_b200.check_status(dev)      # cleared
+    finally:
+        simulst_b200.assume_right_padding(False)
