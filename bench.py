@@ -522,6 +522,8 @@ def side_benchmarks(lib, dev):
                       "ms_per_step": ms, "algorithmic_bytes": alg,
                       "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak,
                       "path": "C ABI, buffers resident: simulst_cif_plan + simulst_cif_fwd + simulst_cif_bwd",
+                      "traffic": sum(ncu_traffic(k) or 0 for k in ("cif_plan_kernel", "cif_fwd_tile_kernel",
+                                                                    "cif_bwd_tile_kernel", "cif_bwd_alpha_kernel")) or None,
                       "python_api": {"value": b * s / (api_ms * 1e-3), "ms_per_step": api_ms,
                                      "roofline_frac": alg / (api_ms * 1e-3) / 1e9 / peak,
                                      "note": "cif_function + autograd backward incl. allocations and the "
