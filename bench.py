@@ -149,6 +149,25 @@ def time_cpu(reps, warmup):
     return elems / best, elems / (total / reps), total / reps, torch.get_num_threads()
 
 
+def time_gpu_eager(dev):
+    """SURVEY 8d "reference GPU path" row: the same restatement of the reference's primitive
+    sequence (oracle port; the reference itself cannot travel to the GPU box) as eager torch-CUDA
+    ops on the full training shape.  A reported baseline next to cpu_baseline, not a product path."""
+    import torch
+    p, e, ga, gb = [t.to(dev) for t in cpu_inputs(N_ROWS)]
+    cpu_port_step(p, e, ga, gb)
+    torch.cuda.synchronize(dev)
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    cpu_port_step(p, e, ga, gb)
+    t1.record()
+    torch.cuda.synchronize(dev)
+    ms = t0.elapsed_time(t1)
+    return {"value": N_ROWS * T * S / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "note": "oracle port as eager torch-CUDA ops, fp32, full training shape, 1 rep after 1 warm-up"}
+
+
 def run_reference(args):
     """`--impl reference`: the reference's own CPU implementation of the path (oracle port: same
     torch ops as codebase/utils/monotonic_attention.py; the Python reference itself cannot travel
@@ -396,6 +415,12 @@ def run_ours(args):
         cpu_base = {"value": mean, "unit": UNIT, "cores": cores, "kind": "port",
                     "sample": f"{CPU_SAMPLE_ROWS} of {N_ROWS} rows (full tgt {T} x src {S}), fp32, "
                               f"fwd+bwd, mean of 2 after 1 warm-up ({sec:.2f} s each)"}
+        try:
+            del gp_host, ge_host
+            torch.cuda.empty_cache()
+            cpu_base["reference_gpu_eager"] = time_gpu_eager(dev)
+        except Exception as exc:  # pragma: no cover
+            cpu_base["reference_gpu_eager"] = {"error": repr(exc)}
 
     if rank == 0:
         peak, peak_src = measured_peak()

@@ -53,7 +53,7 @@ def exclusive_cumprod(t: Tensor, dim: int, eps: float = 1e-10) -> Tensor:
         raise RuntimeError("Cumprod on dimension 3 and more is not implemented")
     lead_shape = list(t.shape)
     lead_shape[dim] = 1
-    padded = torch.cat([torch.ones(lead_shape, dtype=t.dtype), t], dim=dim)
+    padded = torch.cat([torch.ones(lead_shape, dtype=t.dtype, device=t.device), t], dim=dim)
     full = safe_cumprod(padded, dim=dim, eps=eps)
     return full.narrow(dim, 0, t.shape[dim])
 
@@ -68,7 +68,7 @@ def moving_sum(x: Tensor, start_idx: int, end_idx: int) -> Tensor:
     n, t, s = x.shape
     width = start_idx + end_idx - 1
     flat = x.reshape(-1, s).unsqueeze(1)
-    ones = torch.ones(1, 1, width, dtype=x.dtype)
+    ones = torch.ones(1, 1, width, dtype=x.dtype, device=x.device)
     full = torch.nn.functional.conv1d(flat, ones, padding=width).squeeze(1)
     out = full[:, end_idx:-start_idx]
     assert out.shape[1] == s
