@@ -86,6 +86,11 @@ int simulst_mma_set_tma(int enable);
  * fast backward 1.4x faster than the generic kernels.  Returns 0 or E_ARG (mode
  * outside 0..7). */
 int simulst_mma_set_pipeline(int mode);
+/* 1 (default): a call with a padding mask (and no LEFT/RIGHT_PADDING flag) runs as two passes
+ * over disjoint row sets -- rows whose mask is a right-padding mask (j >= len) through the dense
+ * kernels, every other row through the arbitrary-mask kernels; each CTA classifies its own row,
+ * so there is no host read.  0: one pass through the arbitrary-mask kernels. */
+int simulst_mma_set_mask_split(int enable);
 /* 1 = CIF forward/backward through the TMA-staged tile kernels when rows are 16-byte aligned
  * and C <= 512 (default), 0 = always the per-warp kernels (same results bit for bit) */
 int simulst_cif_set_tile(int enable);

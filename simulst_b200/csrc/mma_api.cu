@@ -46,6 +46,18 @@ static int check_device() {
     return c == 1 ? SIMULST_OK : SIMULST_E_ARCH;
 }
 
+static int g_split_masked = 1;     // masked calls: dense pass for right-padded rows + general pass for the rest
+
+// A masked call is split when the dense kernels can take the right-padded rows: hard or
+// infinite-lookback attention, TMA-legal rows that divide evenly among the threads, no
+// left-padding semantics, and no promise flag (with the promise the dense pass runs alone).
+static bool split_masked_call(const MmaParams& prm, int mode, const Config& cfg, bool dense_enabled) {
+    if (!g_split_masked || !dense_enabled || prm.mask == nullptr || mode == kModeSoftCk) return false;
+    if (prm.flags & (SIMULST_MMA_LEFT_PADDING | SIMULST_MMA_RIGHT_PADDING)) return false;
+    if (!prm.tma || !prm.vec_out || prm.S % cfg.vpt != 0 || cfg.threads > 512 || cfg.vpt > 12) return false;
+    return true;
+}
+
 static int mode_of(unsigned flags, int chunk) {
     if (!(flags & SIMULST_MMA_SOFT)) return kModeHard;
     return chunk > 0 ? kModeSoftCk : kModeSoftIL;
@@ -67,6 +79,11 @@ int simulst_mma_set_config(int threads, int vpt) {
 
 int simulst_mma_set_tma(int enable) {
     g_use_tma = enable ? 1 : 0;
+    return SIMULST_OK;
+}
+
+int simulst_mma_set_mask_split(int enable) {
+    g_split_masked = enable ? 1 : 0;
     return SIMULST_OK;
 }
 
@@ -116,11 +133,27 @@ int simulst_mma_train_fwd_delays(const void* p_choose, int p_dtype, const void* 
     const Config cfg = pick_config(S);
     const int mode = mode_of(flags, chunk_size);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    switch (p_dtype) {
-        case SIMULST_F32: return mma_fwd_dispatch_f32(prm, mode, cfg.threads, cfg.vpt, st);
-        case SIMULST_BF16: return mma_fwd_dispatch_bf16(prm, mode, cfg.threads, cfg.vpt, st);
-        default: return mma_fwd_dispatch_f16(prm, mode, cfg.threads, cfg.vpt, st);
+    auto run = [&](const MmaParams& q) {
+        switch (p_dtype) {
+            case SIMULST_F32: return mma_fwd_dispatch_f32(q, mode, cfg.threads, cfg.vpt, st);
+            case SIMULST_BF16: return mma_fwd_dispatch_bf16(q, mode, cfg.threads, cfg.vpt, st);
+            default: return mma_fwd_dispatch_f16(q, mode, cfg.threads, cfg.vpt, st);
+        }
+    };
+    if (split_masked_call(prm, mode, cfg, prm.pipe != 0)) {
+        // pass 1: rows whose mask is a right-padding mask, through the dense kernels;
+        // pass 2: every other row, element-by-element mask handling.  Each CTA decides from its
+        // own row's mask which pass it belongs to, so no host read and no extra buffer.
+        MmaParams a = prm;
+        a.flags |= SIMULST_MMA_RIGHT_PADDING;
+        a.row_filter = 1;
+        const int rc = run(a);
+        if (rc != SIMULST_OK) return rc;
+        MmaParams b = prm;
+        b.row_filter = 2;
+        return run(b);
     }
+    return run(prm);
 }
 
 int simulst_mma_train_bwd(const void* p_choose, int p_dtype, const void* soft_energy, int e_dtype,
@@ -177,11 +210,24 @@ int simulst_mma_train_bwd_delays(const void* p_choose, int p_dtype, const void* 
     const Config cfg = pick_config(S);
     const int mode = mode_of(flags, chunk_size);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    switch (p_dtype) {
-        case SIMULST_F32: return mma_bwd_dispatch_f32(prm, mode, cfg.threads, cfg.vpt, st);
-        case SIMULST_BF16: return mma_bwd_dispatch_bf16(prm, mode, cfg.threads, cfg.vpt, st);
-        default: return mma_bwd_dispatch_f16(prm, mode, cfg.threads, cfg.vpt, st);
+    auto run = [&](const MmaParams& q) {
+        switch (p_dtype) {
+            case SIMULST_F32: return mma_bwd_dispatch_f32(q, mode, cfg.threads, cfg.vpt, st);
+            case SIMULST_BF16: return mma_bwd_dispatch_bf16(q, mode, cfg.threads, cfg.vpt, st);
+            default: return mma_bwd_dispatch_f16(q, mode, cfg.threads, cfg.vpt, st);
+        }
+    };
+    if (split_masked_call(prm, mode, cfg, prm.fast != 0)) {
+        MmaParams a = prm;          // see simulst_mma_train_fwd_delays
+        a.flags |= SIMULST_MMA_RIGHT_PADDING;
+        a.row_filter = 1;
+        const int rc = run(a);
+        if (rc != SIMULST_OK) return rc;
+        MmaParams b = prm;
+        b.row_filter = 2;
+        return run(b);
     }
+    return run(prm);
 }
 
 }  // extern "C"

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : 1)) mma_
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = blockIdx.x;
+    if (row_filtered_out(prm, n)) return;       // this row belongs to the call's other pass
     const int S = prm.S, T_len = prm.T;
     const int j0 = tid * VPT;
     const float eps = prm.eps;

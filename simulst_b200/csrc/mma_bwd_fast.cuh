@@ -393,6 +393,7 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     // uniform branches around the TMA issue code)
     const int warp = __shfl_sync(kFull, tid >> 5, 0);
     const int n = blockIdx.x;
+    if (row_filtered_out(prm, n)) return;       // this row belongs to the call's other pass
     const int S = prm.S, T_len = prm.T;
     const int j0 = tid * VPT;
     const float eps = prm.eps;

@@ -35,7 +35,24 @@ struct MmaParams {
     int vec_out;            // 1: fp32 rows may be accessed as float4
     int pipe;               // 1: software-pipelined kernels (hard / infinite lookback, needs tma)
     int fast;               // 1: dense fast-path backward kernel when the row qualifies
+    int row_filter;         // masked calls only: 0 all rows, 1 only rows whose mask is a right-padding mask
+                            // (j >= len), 2 only the other rows -- the two passes of a masked call
 };
+
+// Block-wide: is this row's padding mask of the form (j >= len), i.e. no live column after a
+// padded one?  One barrier; the result is uniform across the CTA.
+__device__ __forceinline__ bool mask_is_right_padded(const uint8_t* __restrict__ mrow, int S) {
+    bool bad = false;
+    for (int j = threadIdx.x; j + 1 < S; j += blockDim.x) bad = bad || (mrow[j] != 0 && mrow[j + 1] == 0);
+    return __syncthreads_or(bad ? 1 : 0) == 0;
+}
+// Row filter of a masked call split into a dense pass (right-padded rows) and a general pass
+// (the other rows): true when this CTA's row belongs to the other pass.
+__device__ __forceinline__ bool row_filtered_out(const MmaParams& prm, int n) {
+    if (prm.mask == nullptr || prm.row_filter == 0) return false;
+    const bool rp = mask_is_right_padded(prm.mask + (size_t)n * prm.S, prm.S);
+    return (prm.row_filter == 1) != rp;
+}
 
 // Double-buffered per-warp exchange area in shared memory.
 struct Xchg {

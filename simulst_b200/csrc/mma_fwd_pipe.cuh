@@ -97,6 +97,7 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(kFull, tid >> 5, 0)   /* shuffle: known warp-uniform */;
     const int n = blockIdx.x;
+    if (row_filtered_out(prm, n)) return;       // this row belongs to the call's other pass
     const int S = prm.S, T_len = prm.T;
     const int j0 = tid * VPT;
     const float eps = prm.eps;

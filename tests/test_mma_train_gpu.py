@@ -363,3 +363,42 @@ def test_broken_right_padding_promise_is_reported():
         simulst_b200.check_status(dev)      # cleared
     finally:
         simulst_b200.assume_right_padding(False)
+
+
+@pytest.mark.parametrize("soft", [False, True])
+@pytest.mark.parametrize("mp", [False, True])
+def test_masked_call_is_split_by_row_between_dense_and_general_kernels(soft, mp):
+    """Default handling of a padding mask: rows whose mask is a right-padding mask run through the
+    dense kernels, rows with any other mask through the arbitrary-mask kernels (each CTA
+    classifies its own row).  A batch mixing both kinds must give what a single pass through the
+    arbitrary-mask kernels gives, and match the oracle."""
+    from simulst_b200 import _lib
+    lib = _lib.load()
+    n, t, s_len = 8, 6, 1024
+    p, se, mask, ga, gb = _seeded(n, t, s_len, seed=51, masked=True)
+    g = torch.Generator().manual_seed(52)
+    holes = torch.rand(n, s_len, generator=g) < 0.1
+    holes[:4] = False                    # rows 0..3 stay right-padded, rows 4..7 get holes
+    holes[:, 0] = False
+    mask = mask | holes
+    outs = []
+    try:
+        for split in (1, 0):
+            assert lib.simulst_mma_set_mask_split(split) == 0
+            outs.append(_run(p, se if soft else None, mask, mp, 0, soft, ga, gb if soft else None))
+    finally:
+        lib.simulst_mma_set_mask_split(1)
+    scale = max(float(ga.abs().max()), float(gb.abs().max()) if soft else 0.0)
+    for k, (a, b) in enumerate(zip(*outs)):
+        if a is None:
+            assert b is None
+            continue
+        assert torch.equal(a[4:], b[4:]), f"output {k}: rows with holes must come from the same kernel"
+        torch.testing.assert_close(a[:4], b[:4], rtol=5e-6, atol=2e-6 * max(scale, float(b.abs().max())))
+    if not mp:      # with mass preservation the reference indexes src_len - 1, meaningless for masks with holes
+        p_o = p.clone().requires_grad_()
+        se_o = se.clone().requires_grad_() if soft else None
+        a_o, b_o = omma.mma_process_train(p_o, se_o, mask, 1e-6, mp, None)
+        ((a_o * ga).sum() + ((b_o * gb).sum() if soft else 0.0)).backward()
+        assert_parity(outs[0][0], a_o.detach(), "alpha")
+        assert_parity(outs[0][2], p_o.grad, "grad_p", extra_atol=2e-6 * scale)
