@@ -383,7 +383,11 @@ def run_ours(args):
             lens = torch.randint(S // 2, S + 1, (N_ROWS,), generator=gm)
             mask = (torch.arange(S)[None, :] >= lens[:, None]).to(dev).view(torch.uint8).contiguous()
             res = {}
-            for name, fl in (("arbitrary_mask_kernels", flags), ("right_padding_promise", flags | _lib.MMA_RIGHT_PADDING)):
+            for name, fl, split in (("single_pass_arbitrary_mask_kernels", flags, 0),
+                                    ("default_two_passes_split_by_row", flags, 1),
+                                    ("right_padding_promise", flags | _lib.MMA_RIGHT_PADDING, 1)):
+                lib.simulst_mma_set_mask_split(split)
+
                 def step_masked():
                     rc = lib.simulst_mma_train_fwd(p.data_ptr(), _lib.BF16, e.data_ptr(), _lib.BF16, mask.data_ptr(),
                                                    alpha.data_ptr(), beta.data_ptr(), side.data_ptr(),
@@ -406,6 +410,7 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 res[name] = {"ms_per_step": m0.elapsed_time(m1) / 10,
                              "value": elems / (m0.elapsed_time(m1) / 10 * 1e-3), "unit": UNIT}
+            lib.simulst_mma_set_mask_split(1)
             extras["masked_batch"] = {"config": "training shape, right-padded source lengths ~ U[S/2, S] (seed 1236), "
                                                 "elements counted over the full [N,T,S] grid", **res}
         except Exception as exc:  # pragma: no cover
