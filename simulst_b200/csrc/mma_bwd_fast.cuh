@@ -1,8 +1,11 @@
-// MMA training backward, dense fast path: same mathematics and the same six block-wide
-// exchanges per target step as mma_bwd.cuh (see its header for the derivation; SURVEY Appendix
-// A.2-A.4), specialised for the case the training shape hits -- no padding mask, the source row
-// fills the CTA exactly (S == THREADS*VPT), rows staged by TMA, hard or infinite-lookback soft
-// attention -- and written for instruction count, because that kernel is issue bound:
+// MMA training backward, dense fast path: same mathematics as mma_bwd.cuh (see its header for
+// the derivation) in five block-wide exchanges per target step (the
+// product scan and the e-scan share one: the row max is reduced one step ahead), for rows whose
+// threads are wholly inside or wholly outside the row -- S a multiple of the per-thread element
+// count, up to 16 warps x 12 elements (S <= 6144) -- with no padding mask or a right-padding
+// mask (template modes RAGGED / MASKED below), rows staged by TMA, hard or infinite-lookback soft
+// attention.  Everything else (other masks, chunkwise windows, unaligned rows) stays with the
+// generic kernel.  Written for instruction count, because that kernel is issue bound:
 //   * element-wise arithmetic on float2 pairs (FADD2 / FMUL2 / FFMA2: one issue slot per two
 //     source positions); only the thread-local scan chains stay scalar;
 //   * warp scans use the shuffle's own predicate (no lane compares, no selects), and the scans
