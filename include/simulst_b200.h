@@ -64,6 +64,7 @@ extern "C" {
                                             and MMACriterion assume); lets masked rows take the dense
                                             backward kernel instead of the arbitrary-mask one */
 #define SIMULST_MMA_MAX_SRC 16384        /* longest source row a single CTA keeps on chip */
+#define SIMULST_SOFT_ATTENTION_MAX_SRC 9600 /* stand-alone simulst_soft_attention_*: 6 fp32 rows on chip */
 
 int simulst_version(void);
 const char* simulst_error_string(int code);
@@ -79,12 +80,12 @@ int simulst_mma_set_config(int threads, int vpt);
 /* 1 = stage rows with TMA bulk copies when alignment allows (default), 0 = cooperative loads */
 int simulst_mma_set_tma(int enable);
 /* Kernel choice for hard / infinite-lookback attention when rows can be TMA-staged.  Bit 0:
- * software-pipelined forward kernel, bit 1: software-pipelined backward kernel, bit 2: dense
- * fast-path backward kernel for unmasked rows that fill the CTA exactly (S = 256, 512, 1024,
- * 2048; takes precedence over bit 1 when the row qualifies); cleared bits select the generic
- * (one scan per barrier) kernels.  Default 5: on B200 the pipelined forward is 1.3x and the
- * fast backward 1.4x faster than the generic kernels.  Returns 0 or E_ARG (mode
- * outside 0..7). */
+ * software-pipelined forward kernel; bit 2: dense fast-path backward kernel (rows that are
+ * unmasked or right-padded and split evenly among the CTA's threads); cleared bits select the
+ * generic (one scan per barrier) kernels.  Bit 1 is accepted and ignored (it selected a
+ * pipelined backward that was slower than both alternatives and has been removed).  Default 5:
+ * on B200 the pipelined forward is 1.3x and the fast backward 1.4x faster than the generic
+ * kernels.  Returns 0 or E_ARG (mode outside 0..7). */
 int simulst_mma_set_pipeline(int mode);
 /* 1 (default): a call with a padding mask (and no LEFT/RIGHT_PADDING flag) runs as two passes
  * over disjoint row sets -- rows whose mask is a right-padding mask (j >= len) through the dense
@@ -178,6 +179,27 @@ int simulst_mma_train_bwd_delays(const void* p_choose, int p_dtype,
                                  void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Latency loss next to the expected-delay epilogue.
+ * DifferentiableAverageLagging as called by MMACriterion.compute_latency_loss
+ * (codebase/criterion/mma_criterion.py:172-177) and CIFCriterion.compute_latency_loss
+ * (codebase/criterion/cif_criterion.py:211-216); the function itself is SimulEval's
+ * (simuleval.metrics.latency, not vendored by the reference):
+ *     g'(0) = g(0), g'(i) = max(g'(i-1) + 1/gamma, g(i)), DAL = sum_i (g'(i) - i/gamma) / |Y|,
+ *     gamma = ref_len / src_len (ref_lens given) or |Y| / src_len.
+ *   delays               [N,T] fp32   expected delays (simulst_mma_train_fwd_delays / CIF delays)
+ *   src_lens, ref_lens   [N] int64    ref_lens may be NULL
+ *   target_padding_mask  [N,T] uint8  non-zero = padded target position; NULL = none
+ *   dal                  [N] fp32 out
+ * One warp per row, T sequential steps instead of ~3T launches.  T <= SIMULST_DAL_MAX_TGT. */
+#define SIMULST_DAL_MAX_TGT 1024
+int simulst_dal_fwd(const float* delays, const int64_t* src_lens, const int64_t* ref_lens,
+                    const uint8_t* target_padding_mask, float* dal, int N, int T, void* stream);
+/* grad_dal [N] fp32 -> grad_delays [N,T] fp32 (recomputes the recurrence). */
+int simulst_dal_bwd(const float* delays, const int64_t* src_lens, const int64_t* ref_lens,
+                    const uint8_t* target_padding_mask, const float* grad_dal,
+                    float* grad_delays, int N, int T, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Stand-alone pieces (same math, rows independent): used when the reference functions are
  * called one by one rather than through monotonic_attention_process_train.
  */
@@ -216,6 +238,13 @@ int simulst_moving_sum(const void* x, void* out, int dtype, long long rows, int 
  * (functions.py:48-66). */
 int simulst_exclusive_cumprod(const void* x, void* out, int dtype, long long rows, int S,
                               float eps, int inclusive, unsigned* status, void* stream);
+
+/* Autograd of the two functions above (the reference composes log / cumsum / exp, which torch
+ * differentiates): grad_x_k = sum_{j >= k + (inclusive ? 0 : 1)} grad_y_j * y_j / (x_k + eps),
+ * y = the forward output.  The backward of moving_sum is moving_sum itself with start_idx and
+ * end_idx exchanged. */
+int simulst_cumprod_bwd(const void* x, const void* y, const void* grad_y, void* grad_x, int dtype,
+                        long long rows, int S, float eps, int inclusive, void* stream);
 
 /* learnable_p_choose (codebase/utils/p_choose_strategy.py:56-76):
  * out = sigmoid(energy + noise), noise may be NULL (eval).  Same dtype in and out; the

@@ -24,6 +24,7 @@ MMA_ENERGY_F16_FILL = 4
 MMA_LEFT_PADDING = 8
 MMA_RIGHT_PADDING = 16
 MMA_MAX_SRC = 16384
+SOFT_ATTENTION_MAX_SRC = 9600      # stand-alone soft attention: 6 fp32 rows + scratch in 227 KB
 
 _lib = None
 _load_error = None
@@ -56,6 +57,9 @@ SIGNATURES = {
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_int, c_void_p, c_int,
                                              c_int, c_int, c_int, c_float, c_int, c_uint, c_void_p]),
+    "simulst_dal_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "simulst_dal_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                c_void_p]),
     "simulst_soft_attention_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                            c_int, c_int, c_int, c_float, c_int, c_uint,
                                            c_void_p, c_void_p]),
@@ -70,6 +74,8 @@ SIGNATURES = {
                                    c_void_p]),
     "simulst_exclusive_cumprod": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_int, c_float,
                                           c_int, c_void_p, c_void_p]),
+    "simulst_cumprod_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_int, c_float,
+                                    c_int, c_void_p]),
     "simulst_p_choose": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p]),
     "simulst_mma_step": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_int, c_int, c_uint, c_void_p]),

@@ -351,6 +351,27 @@ exclusive_cumprod_kernel(const T* __restrict__ x, T* __restrict__ out, int S, fl
     flag_status(status, bits);
 }
 
+// Autograd of exclusive_cumprod / safe_cumprod (the reference's versions are differentiable
+// compositions log -> cumsum -> exp, functions.py:20-66): with y the forward output,
+//   d y_j / d x_k = y_j / (x_k + eps)  for j >= k + shift   (shift = 1 exclusive, 0 inclusive)
+// so grad_x_k = suffix_{j >= k+shift}(g_j * y_j) / (x_k + eps).
+template <typename T>
+__global__ void __launch_bounds__(kRowThreads)
+cumprod_bwd_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ g,
+                   T* __restrict__ gx, int S, float eps, int inclusive) {
+    extern __shared__ float sm[];
+    float* a = sm;
+    float* scratch = sm + S + 1;
+    const size_t row = blockIdx.x;
+    for (int j = threadIdx.x; j < S; j += kRowThreads) a[j] = to_f32<T>(g[row * S + j]) * to_f32<T>(y[row * S + j]);
+    if (threadIdx.x == 0) a[S] = 0.f;
+    __syncthreads();
+    block_scan_smem<true>(a, S + 1, scratch);
+    const int shift = inclusive ? 0 : 1;
+    for (int k = threadIdx.x; k < S; k += kRowThreads)
+        gx[row * S + k] = from_f32<T>(a[k + shift] / (to_f32<T>(x[row * S + k]) + eps));
+}
+
 // ---------------------------------------------------------------------------- p_choose
 template <typename T>
 __global__ void p_choose_kernel(const T* __restrict__ energy, const T* __restrict__ noise,
@@ -478,6 +499,25 @@ int simulst_exclusive_cumprod(const void* x, void* out, int dtype, long long row
         }
         kern<<<(unsigned)rows, kRowThreads, smem, (cudaStream_t)stream>>>((const T*)x, (T*)out, S, eps,
                                                                           inclusive, status);
+        return check_launch();
+    });
+}
+
+int simulst_cumprod_bwd(const void* x, const void* y, const void* grad_y, void* grad_x, int dtype, long long rows,
+                        int S, float eps, int inclusive, void* stream) {
+    if (!x || !y || !grad_y || !grad_x || !valid_dtype(dtype)) return SIMULST_E_ARG;
+    if (rows < 0 || S < 0 || S > 48000) return SIMULST_E_SHAPE;
+    if (rows == 0 || S == 0) return SIMULST_OK;
+    const size_t smem = ((size_t)S + 1 + kRowThreads + 16) * sizeof(float);
+    return dispatch1(dtype, [&](auto t) {
+        using T = decltype(t);
+        auto kern = cumprod_bwd_kernel<T>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return (int)SIMULST_E_SHAPE;
+        }
+        kern<<<(unsigned)rows, kRowThreads, smem, (cudaStream_t)stream>>>((const T*)x, (const T*)y, (const T*)grad_y,
+                                                                          (T*)grad_x, S, eps, inclusive);
         return check_launch();
     });
 }

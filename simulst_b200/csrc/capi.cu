@@ -19,7 +19,7 @@ const char* simulst_error_string(int code) {
     }
 }
 
-long long simulst_launch_count(void) { return LaunchCounter::value(); }
-void simulst_reset_launch_count(void) { LaunchCounter::value() = 0; }
+long long simulst_launch_count(void) { return LaunchCounter::value().load(std::memory_order_relaxed); }
+void simulst_reset_launch_count(void) { LaunchCounter::value().store(0, std::memory_order_relaxed); }
 
 }  // extern "C"

@@ -477,9 +477,9 @@ static int set_smem(K kern, size_t bytes) {
 using namespace simulst;
 
 // development / test switch: route simulst_cif_fwd/_bwd through the per-warp fallback kernels
-static int g_cif_force_fallback = 0;
+static std::atomic<int> g_cif_force_fallback{0};   // tuning knobs: relaxed atomics, see mma_api.cu
 // tuning overrides (0 = automatic): frames per forward tile chunk, frames per backward tile
-static int g_cif_fc = 0, g_cif_fr = 0;
+static std::atomic<int> g_cif_fc{0}, g_cif_fr{0};
 
 extern "C" {
 
@@ -545,7 +545,8 @@ int simulst_cif_fwd(const void* input, int x_dtype, const float* csum, const flo
                 constexpr int NP = decltype(np)::value;
                 if (tile) {
                     const size_t row_bytes = (size_t)C * sizeof(TX);
-                    const int FC = g_cif_fc > 0 ? g_cif_fc : (int)std::max<size_t>(8, 48 * 1024 / row_bytes);
+                    const int fc_forced = g_cif_fc.load(std::memory_order_relaxed);
+                    const int FC = fc_forced > 0 ? fc_forced : (int)std::max<size_t>(8, 48 * 1024 / row_bytes);
                     const size_t smem = kTileHeader + (size_t)FC * row_bytes;
                     auto kern = cif_fwd_tile_kernel<TX, TA, NP>;
                     if (int rc = set_smem(kern, smem)) return rc;
@@ -595,7 +596,7 @@ int simulst_cif_bwd(const void* input, int x_dtype, const float* csum, const flo
                     const size_t row_bytes = (size_t)C * sizeof(TX);
                     int FR = (int)(32 * 1024 / row_bytes) / kTileWarps * kTileWarps;
                     FR = std::max(kTileWarps, std::min(64, FR));
-                    if (g_cif_fr > 0) FR = g_cif_fr;
+                    if (const int fr_forced = g_cif_fr.load(std::memory_order_relaxed); fr_forced > 0) FR = fr_forced;
                     const int GR = FR / 2 + 2;
                     const size_t smem = kTileHeader + (size_t)(FR + GR) * row_bytes;
                     auto kern = cif_bwd_tile_kernel<TX, TA, NP>;

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/simulst_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -298,8 +300,8 @@ __device__ __forceinline__ unsigned prob_bits(float v) {
 
 // ------------------------------------------------------------------ host side
 struct LaunchCounter {
-    static long long& value() {
-        static long long v = 0;
+    static std::atomic<long long>& value() {
+        static std::atomic<long long> v{0};
         return v;
     }
 };
@@ -321,7 +323,7 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 }
 
 inline int check_launch() {
-    LaunchCounter::value() += 1;
+    LaunchCounter::value().fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SIMULST_OK : SIMULST_E_LAUNCH;
 }

@@ -1,12 +1,18 @@
 // C-ABI entry points of the MMA training path (see include/simulst_b200.h).
+#include <atomic>
+
 #include "mma_common.cuh"
 #include "mma_dispatch.h"
 
 namespace simulst {
 
-static int g_cfg_threads = 0, g_cfg_vpt = 0;   // 0 = automatic
-static int g_use_tma = 1;
-static int g_use_pipe = 5;   // bit 0: pipelined forward, bit 1: pipelined backward, bit 2: dense fast-path backward
+// Tuning overrides (development / test knobs; every default is the measured best).  Each is one
+// relaxed atomic word: a setter racing with a call on another thread changes WHICH kernel variant
+// that call picks, never its results (all variants pass the same parity tests), and every entry
+// point snapshots the words once at its top, so one call never mixes two settings.
+static std::atomic<int> g_cfg{0};          // (threads << 8) | vpt; 0 = automatic
+static std::atomic<int> g_use_tma{1};
+static std::atomic<int> g_use_pipe{5};     // bit 0: pipelined forward, bit 1: pipelined backward, bit 2: dense fast-path backward
 
 struct Config { int threads, vpt; };
 
@@ -19,7 +25,8 @@ static bool config_exists(int threads, int vpt) {
 
 // Smallest configuration that keeps a whole source row on chip.
 static Config pick_config(int S) {
-    if (g_cfg_threads > 0 && g_cfg_threads * g_cfg_vpt >= S) return {g_cfg_threads, g_cfg_vpt};
+    const int forced = g_cfg.load(std::memory_order_relaxed);
+    if (forced != 0 && (forced >> 8) * (forced & 255) >= S) return {forced >> 8, forced & 255};
     if (S <= 128) return {32, 4};
     if (S <= 256) return {32, 8};
     if (S <= 512) return {64, 8};
@@ -46,13 +53,13 @@ static int check_device() {
     return c == 1 ? SIMULST_OK : SIMULST_E_ARCH;
 }
 
-static int g_split_masked = 1;     // masked calls: dense pass for right-padded rows + general pass for the rest
+static std::atomic<int> g_split_masked{1};     // masked calls: dense pass for right-padded rows + general pass for the rest
 
 // A masked call is split when the dense kernels can take the right-padded rows: hard or
 // infinite-lookback attention, TMA-legal rows that divide evenly among the threads, no
 // left-padding semantics, and no promise flag (with the promise the dense pass runs alone).
 static bool split_masked_call(const MmaParams& prm, int mode, const Config& cfg, bool dense_enabled) {
-    if (!g_split_masked || !dense_enabled || prm.mask == nullptr || mode == kModeSoftCk) return false;
+    if (!g_split_masked.load(std::memory_order_relaxed) || !dense_enabled || prm.mask == nullptr || mode == kModeSoftCk) return false;
     if (prm.flags & (SIMULST_MMA_LEFT_PADDING | SIMULST_MMA_RIGHT_PADDING)) return false;
     if (!prm.tma || !prm.vec_out || prm.S % cfg.vpt != 0 || cfg.threads > 512 || cfg.vpt > 12) return false;
     return true;
@@ -70,26 +77,25 @@ using namespace simulst;
 extern "C" {
 
 int simulst_mma_set_config(int threads, int vpt) {
-    if (threads == 0 && vpt == 0) { g_cfg_threads = g_cfg_vpt = 0; return SIMULST_OK; }
+    if (threads == 0 && vpt == 0) { g_cfg.store(0, std::memory_order_relaxed); return SIMULST_OK; }
     if (!config_exists(threads, vpt)) return SIMULST_E_ARG;
-    g_cfg_threads = threads;
-    g_cfg_vpt = vpt;
+    g_cfg.store((threads << 8) | vpt, std::memory_order_relaxed);
     return SIMULST_OK;
 }
 
 int simulst_mma_set_tma(int enable) {
-    g_use_tma = enable ? 1 : 0;
+    g_use_tma.store(enable ? 1 : 0, std::memory_order_relaxed);
     return SIMULST_OK;
 }
 
 int simulst_mma_set_mask_split(int enable) {
-    g_split_masked = enable ? 1 : 0;
+    g_split_masked.store(enable ? 1 : 0, std::memory_order_relaxed);
     return SIMULST_OK;
 }
 
 int simulst_mma_set_pipeline(int mode) {
     if (mode < 0 || mode > 7) return SIMULST_E_ARG;
-    g_use_pipe = mode;
+    g_use_pipe.store(mode, std::memory_order_relaxed);
     return SIMULST_OK;
 }
 
@@ -125,10 +131,11 @@ int simulst_mma_train_fwd_delays(const void* p_choose, int p_dtype, const void* 
     prm.delays = expected_delays;
     prm.N = N; prm.T = T; prm.S = S; prm.eps = eps; prm.chunk = chunk_size; prm.flags = flags;
     prm.status = status;
-    prm.tma = g_use_tma && ((size_t)S * esz) % 16 == 0 && aligned(p_choose, 16) &&
+    const int use_pipe = g_use_pipe.load(std::memory_order_relaxed);
+    prm.tma = g_use_tma.load(std::memory_order_relaxed) && ((size_t)S * esz) % 16 == 0 && aligned(p_choose, 16) &&
               (!soft || aligned(soft_energy, 16));
     prm.vec_out = (S % 4 == 0) && aligned(alpha, 16) && (!soft || aligned(beta, 16));
-    prm.pipe = g_use_pipe & 1;
+    prm.pipe = use_pipe & 1;
 
     const Config cfg = pick_config(S);
     const int mode = mode_of(flags, chunk_size);
@@ -202,10 +209,11 @@ int simulst_mma_train_bwd_delays(const void* p_choose, int p_dtype, const void* 
                      (grad_alpha == nullptr || aligned(grad_alpha, 16)) &&
                      (grad_beta == nullptr || aligned(grad_beta, 16)) && aligned(grad_p, 16) &&
                      (!soft || aligned(grad_energy, 16));
-    prm.tma = g_use_tma && ((size_t)S * esz) % 16 == 0 && a16;
+    const int use_pipe = g_use_pipe.load(std::memory_order_relaxed);
+    prm.tma = g_use_tma.load(std::memory_order_relaxed) && ((size_t)S * esz) % 16 == 0 && a16;
     prm.vec_out = ((size_t)S * esz) % 16 == 0 && (S % 4 == 0) && a16;
-    prm.pipe = (g_use_pipe >> 1) & 1;
-    prm.fast = (g_use_pipe >> 2) & 1;
+    prm.pipe = (use_pipe >> 1) & 1;
+    prm.fast = (use_pipe >> 2) & 1;
 
     const Config cfg = pick_config(S);
     const int mode = mode_of(flags, chunk_size);

@@ -1,7 +1,6 @@
 // Instantiations of the MMA backward kernel for ONE activation dtype (selected with
 // -DSIMULST_INST_DTYPE=0|1|2 so the three dtypes compile in parallel).
 #include "mma_bwd.cuh"
-#include "mma_bwd_pipe.cuh"
 #include "mma_bwd_fast.cuh"
 #include "mma_fwd_pipe.cuh"
 #include "mma_dispatch.h"
@@ -26,13 +25,6 @@ int INST_NAME(const MmaParams& prm, int mode, int threads, int vpt, cudaStream_t
             const int rc = mode == kModeHard ? launch_mma_bwd_fast<TH, VP, InstT, false>(prm, stream) \
                                              : launch_mma_bwd_fast<TH, VP, InstT, true>(prm, stream); \
             if (rc != 1) return rc;             /* 1 = row does not qualify for the dense fast path */ \
-        }                                                                                 \
-        if constexpr (TH <= 256) {      /* the pipelined backward is validated up to 8 warps */ \
-            if (prm.tma && prm.pipe && mode != kModeSoftCk && prm.g_delays == nullptr) {                             \
-                const int rc = mode == kModeHard ? launch_mma_bwd_pipe<TH, VP, InstT, false>(prm, stream) \
-                                                 : launch_mma_bwd_pipe<TH, VP, InstT, true>(prm, stream); \
-                if (rc != 1) return rc;         /* 1 = row too long for the pipelined kernel */ \
-            }                                                                             \
         }                                                                                 \
         switch (mode) {                                                                   \
             case kModeHard: return launch_mma_bwd<TH, VP, InstT, kModeHard>(prm, stream); \

@@ -170,13 +170,23 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
     const int nl = MASKED ? max(0, min(VPT, last + 1 - j0)) : VPT;
     (void)nl;
     if constexpr (FULL && MASKED) {
-        // the promise is checked, not trusted: a mask that is not (j >= len) flags the status word
-        if (j0 < S && prm.status != nullptr) {
+        // the promise is checked, not trusted: a row whose mask is not (j >= len) flags the status
+        // word AND has its outputs poisoned with NaN, so a broken promise cannot train on silently
+        // even when nobody reads the (lazily inspected) status word
+        bool ok = true;
+        if (j0 < S) {
             const uint8_t* mrow = prm.mask + (size_t)n * S + j0;
-            bool ok = true;
 #pragma unroll
             for (int k = 0; k < VPT; ++k) ok = ok && ((mrow[k] == 0) == (k < nl));
-            if (!ok) atomicOr(prm.status, SIMULST_ST_NOT_RIGHT_PADDED);
+        }
+        if (__syncthreads_or(ok ? 0 : 1)) {
+            if (tid == 0 && prm.status != nullptr) atomicOr(prm.status, SIMULST_ST_NOT_RIGHT_PADDED);
+            const float qnan = __int_as_float(0x7fc00000);
+            for (size_t q = tid; q < (size_t)T_len * S; q += THREADS) {
+                g_alpha[q] = qnan;
+                if (SOFT) g_beta[q] = qnan;
+            }
+            return;
         }
     }
     int k_last = -1;

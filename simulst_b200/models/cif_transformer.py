@@ -10,20 +10,30 @@ from torch import Tensor
 from .torch_cif import cif_function
 
 
+def _takes_incremental_state(module) -> bool:
+    """CausalConvTBC (modules/causal_conv.py:80-98) is ``make_causal(ConvTBC)`` decorated with
+    ``with_incremental_state``; LayerNorm / GELU / Dropout / Linear are not."""
+    return type(module).__name__ == "CausalConvTBC" or hasattr(module, "get_incremental_state")
+
+
 class B200CIFLayerMixin:
     """Expects the attributes of the reference CIFLayer: alpha_proj, sg_alpha, beta, tail_thres,
     get_incremental_state / set_incremental_state."""
 
-    def _integration_weights(self, x, incremental_state=None):
-        """reference :158-161 (train) / :202-208 (infer): sigmoid(alpha_proj(x)) -> (B, S)."""
-        if incremental_state is None:
+    def _integration_weights(self, x, incremental_state=None, streaming=False):
+        """reference :157-161 (train) / :201-208 (infer): sigmoid(alpha_proj(x)) -> (B, S).
+        In streaming mode the reference hands ``incremental_state`` (unchanged, None included) to
+        the ``CausalConvTBC`` members of ``alpha_proj`` and calls the others plainly; the members
+        are recognised by what makes them streamable -- the incremental-state accessors that
+        fairseq's ``with_incremental_state`` puts on the class -- not by catching TypeError."""
+        if not streaming:
             alpha = self.alpha_proj(x.detach() if self.sg_alpha else x)
         else:
             alpha = x
             for m in self.alpha_proj:
-                try:
+                if _takes_incremental_state(m):
                     alpha = m(alpha, incremental_state)
-                except TypeError:
+                else:
                     alpha = m(alpha)
         return alpha.transpose(1, 0).sigmoid().squeeze(-1)
 
@@ -49,7 +59,7 @@ class B200CIFLayerMixin:
         chunk_len, bsz, C = x.size()
         if bsz > 1:
             raise NotImplementedError("batched infer not supported for now.")
-        alpha = self._integration_weights(x, incremental_state if incremental_state is not None else {})
+        alpha = self._integration_weights(x, incremental_state, streaming=True)
         cached_state = self.get_incremental_state(incremental_state, "cif_state")
         if cached_state is None:
             cached_state = {}
@@ -86,13 +96,20 @@ def cif_layer_forward(x: Tensor, alpha: Tensor, beta: float, tail_thres: float,
 def cif_layer_infer(x: Tensor, alpha: Tensor, cached_state: Dict[str, Optional[Tensor]],
                     beta: float, tail_thres: float, finish: bool = False):
     """reference :210-261 from the point where `alpha` is the (1, chunk) sigmoid output.
-    Mutates `cached_state` (prev_weight (B,1), prev_feat (B,1,C))."""
+    Mutates `cached_state` (prev_weight (B,1), prev_feat (B,1,C)).
+
+    Upstream quirk, REPRODUCED: between chunks ``tail_thres`` is 0, so the
+    tail always "fires" and is rescaled by ``beta / tail_weight`` (cif.py:170-178); a chunk whose
+    accumulated weight ends exactly on a firing boundary (``tail_weight == 0``) therefore carries
+    ``0 * inf = NaN`` features with weight 0 into the next chunk, in the reference and here alike
+    (``tests/test_reference_classes_gpu.py::test_cif_infer_zero_tail_weight_quirk``).  Guarding it
+    would change results a fairseq checkpoint was trained against; a caller that wants the guard
+    can zero ``prev_feat`` where ``prev_weight == 0``."""
     bsz = x.size(1)
     x = x.transpose(1, 0)
     if (
         "prev_weight" in cached_state
-        and cached_state["prev_weight"] is not None
-        and cached_state["prev_weight"].numel() > 0
+        and cached_state["prev_weight"].numel() > 0     # None after finish=True: raises, as upstream (:254)
     ):
         # leftover features with weight: treated as a single source feature
         alpha = torch.cat((cached_state["prev_weight"], alpha), dim=1)

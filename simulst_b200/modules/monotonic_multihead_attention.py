@@ -132,7 +132,12 @@ class B200MonotonicAttentionMixin:
 
 
 def patch_monotonic_attention(cls):
-    """Replace the two method bodies of an existing reference attention class in place."""
+    """Replace the two method bodies of an existing reference attention class in place (and add
+    the helper they share).  Everything else of the class -- projections, energy bmm's,
+    ``forward``, incremental-state plumbing -- stays the reference's."""
     cls.monotonic_attention_process_train = B200MonotonicAttentionMixin.monotonic_attention_process_train
     cls.monotonic_attention_process_infer = B200MonotonicAttentionMixin.monotonic_attention_process_infer
+    cls._alignment = B200MonotonicAttentionMixin._alignment
+    if not hasattr(cls, "expected_delays"):
+        cls.expected_delays = None
     return cls

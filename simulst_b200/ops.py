@@ -62,8 +62,11 @@ class MMATrainFunction(torch.autograd.Function):
             flags |= _lib.MMA_RIGHT_PADDING
         alpha = torch.empty((n, t, s), dtype=torch.float32, device=dev)
         beta = torch.empty((n, t, s), dtype=torch.float32, device=dev) if soft else None
-        side = torch.empty((n, t, 2), dtype=torch.float32, device=dev) if mass_preservation else None
-        delays = torch.empty((n, t), dtype=torch.float32, device=dev) if with_delays else None
+        # a row whose mask leaves no live column has no mass-preservation column: the kernels
+        # write nothing for it, so with a mask these two small buffers start as zeros
+        small = torch.zeros if mask is not None else torch.empty
+        side = small((n, t, 2), dtype=torch.float32, device=dev) if mass_preservation else None
+        delays = small((n, t), dtype=torch.float32, device=dev) if with_delays else None
         status = _lib.status_word(dev)
         chunk = int(chunk_size) if chunk_size else 0
         with torch.cuda.device(dev):
@@ -152,6 +155,11 @@ class SoftAttentionFunction(torch.autograd.Function):
         n, t, s = alpha.shape
         if tuple(soft_energy.shape) != (n, t, s):
             raise ValueError("soft_energy must have the shape of alpha")
+        if s > _lib.SOFT_ATTENTION_MAX_SRC:
+            raise ValueError(
+                f"stand-alone expected_soft_attention keeps 6 fp32 rows on chip: src_len {s} exceeds "
+                f"{_lib.SOFT_ATTENTION_MAX_SRC}; the fused operator (ops.mma_train) handles rows up to "
+                f"{_lib.MMA_MAX_SRC}")
         a = alpha.contiguous()
         e = soft_energy.contiguous()
         mask = _mask_u8(padding_mask, n, s, dev)
@@ -238,35 +246,88 @@ class MassPreservationFunction(torch.autograd.Function):
         return gout.to(in_dtype), None, None
 
 
-def moving_sum(x: Tensor, start_idx: int, end_idx: int) -> Tensor:
-    """functions.py:69-125 (forward only: the reference uses it inside expected_soft_attention,
-    whose gradient is SoftAttentionFunction's)."""
+class MovingSumFunction(torch.autograd.Function):
+    """moving_sum (functions.py:69-125).  The reference builds it from conv1d, so it is
+    differentiable there; the adjoint of a sliding-window sum is the mirrored window:
+    grad_x = moving_sum(grad_out, end_idx, start_idx)."""
+
+    @staticmethod
+    def forward(ctx, x, start_idx, end_idx):
+        ctx.window = (int(start_idx), int(end_idx))
+        return _moving_sum_raw(x, int(start_idx), int(end_idx))
+
+    @staticmethod
+    def backward(ctx, g):
+        start_idx, end_idx = ctx.window
+        return _moving_sum_raw(g, end_idx, start_idx), None, None
+
+
+def _moving_sum_raw(x: Tensor, start_idx: int, end_idx: int) -> Tensor:
     lib = _lib.load()
     dev = _lib.require_cuda(x)
-    assert start_idx > 0 and end_idx > 0
     n, t, s = x.shape
     xc = x.contiguous()
     out = torch.empty_like(xc)
     with torch.cuda.device(dev):
         rc = lib.simulst_moving_sum(_lib.ptr(xc), _lib.ptr(out), _lib.dtype_enum(xc.dtype), n * t, s,
-                                    int(start_idx), int(end_idx), _lib.stream_ptr(dev))
+                                    start_idx, end_idx, _lib.stream_ptr(dev))
     _lib.check(rc, "simulst_moving_sum")
     return out
 
 
-def exclusive_cumprod_lastdim(x: Tensor, eps: float, inclusive: bool = False) -> Tensor:
-    lib = _lib.load()
-    dev = _lib.require_cuda(x)
-    s = x.shape[-1]
-    xc = x.contiguous()
-    out = torch.empty_like(xc)
-    rows = xc.numel() // max(s, 1)
-    with torch.cuda.device(dev):
-        rc = lib.simulst_exclusive_cumprod(_lib.ptr(xc), _lib.ptr(out), _lib.dtype_enum(xc.dtype), rows, s,
-                                           float(eps), 1 if inclusive else 0,
-                                           _lib.ptr(_lib.status_word(dev)), _lib.stream_ptr(dev))
-    _lib.check(rc, "simulst_exclusive_cumprod")
-    _lib.maybe_check(dev)
+def moving_sum(x: Tensor, start_idx: int, end_idx: int) -> Tensor:
+    """functions.py:69-125 over the last axis of a [N, T, S] tensor; differentiable like the
+    reference's conv1d formulation."""
+    assert start_idx > 0 and end_idx > 0
+    return MovingSumFunction.apply(x, start_idx, end_idx)
+
+
+class CumprodFunction(torch.autograd.Function):
+    """exclusive_cumprod / safe_cumprod along the last axis (functions.py:20-66), differentiable
+    like the reference's exp(cumsum(log(x + eps)))."""
+
+    @staticmethod
+    def forward(ctx, x, eps, inclusive, status):
+        lib = _lib.load()
+        dev = _lib.require_cuda(x)
+        s = x.shape[-1]
+        xc = x.contiguous()
+        out = torch.empty_like(xc)
+        rows = xc.numel() // max(s, 1)
+        with torch.cuda.device(dev):
+            rc = lib.simulst_exclusive_cumprod(_lib.ptr(xc), _lib.ptr(out), _lib.dtype_enum(xc.dtype), rows, s,
+                                               float(eps), 1 if inclusive else 0,
+                                               _lib.ptr(status), _lib.stream_ptr(dev))
+        _lib.check(rc, "simulst_exclusive_cumprod")
+        ctx.save_for_backward(xc, out)
+        ctx.cfg = (float(eps), bool(inclusive))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        xc, out = ctx.saved_tensors
+        eps, inclusive = ctx.cfg
+        dev = xc.device
+        s = xc.shape[-1]
+        rows = xc.numel() // max(s, 1)
+        gc = g.contiguous().to(xc.dtype)
+        gx = torch.empty_like(xc)
+        with torch.cuda.device(dev):
+            rc = lib.simulst_cumprod_bwd(_lib.ptr(xc), _lib.ptr(out), _lib.ptr(gc), _lib.ptr(gx),
+                                         _lib.dtype_enum(xc.dtype), rows, s, eps, 1 if inclusive else 0,
+                                         _lib.stream_ptr(dev))
+        _lib.check(rc, "simulst_cumprod_bwd")
+        return gx, None, None, None
+
+
+def exclusive_cumprod_lastdim(x: Tensor, eps: float, inclusive: bool = False,
+                              status: Optional[Tensor] = None) -> Tensor:
+    """`status`: device word that receives SIMULST_ST_NEGPROD (default: the per-device word)."""
+    if status is None:
+        status = _lib.status_word(_lib.require_cuda(x))
+    out = CumprodFunction.apply(x, eps, inclusive, status)
+    _lib.maybe_check(x.device)
     return out
 
 
@@ -414,3 +475,51 @@ class CIFFunction(torch.autograd.Function):
                                      _lib.stream_ptr(dev))
         _lib.check(rc, "simulst_cif_bwd")
         return gx, ga, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------- latency loss
+class DALFunction(torch.autograd.Function):
+    """DifferentiableAverageLagging(delays, src_lens, ref_lens, target_padding_mask) as the
+    reference's criteria call it (codebase/criterion/mma_criterion.py:172-177,
+    codebase/criterion/cif_criterion.py:211-216).  Returns [N, 1] like SimulEval's function."""
+
+    @staticmethod
+    def forward(ctx, delays, src_lens, ref_lens, target_padding_mask):
+        lib = _lib.load()
+        dev = _lib.require_cuda(delays, src_lens, ref_lens, target_padding_mask)
+        if delays.dim() != 2:
+            raise ValueError("delays must be [N, tgt_len]")
+        n, t = delays.shape
+        d = delays.contiguous().float()
+        src = src_lens.reshape(n).long().contiguous()
+        ref = ref_lens.reshape(n).long().contiguous() if ref_lens is not None else None
+        mask = _mask_u8(target_padding_mask, n, t, dev)
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.simulst_dal_fwd(_lib.ptr(d), _lib.ptr(src), _lib.ptr(ref), _lib.ptr(mask), _lib.ptr(out),
+                                     n, t, _lib.stream_ptr(dev))
+        _lib.check(rc, "simulst_dal_fwd")
+        ctx.save_for_backward(d, src, ref, mask)
+        ctx.in_dtype = delays.dtype
+        return out.view(n, 1).to(delays.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        d, src, ref, mask = ctx.saved_tensors
+        n, t = d.shape
+        dev = d.device
+        gd = g.reshape(n).contiguous().float()
+        out = torch.empty_like(d)
+        with torch.cuda.device(dev):
+            rc = lib.simulst_dal_bwd(_lib.ptr(d), _lib.ptr(src), _lib.ptr(ref), _lib.ptr(mask), _lib.ptr(gd),
+                                     _lib.ptr(out), n, t, _lib.stream_ptr(dev))
+        _lib.check(rc, "simulst_dal_bwd")
+        return out.to(ctx.in_dtype), None, None, None
+
+
+def differentiable_average_lagging(delays: Tensor, src_lens: Tensor, ref_lens: Optional[Tensor] = None,
+                                   target_padding_mask: Optional[Tensor] = None) -> Tensor:
+    """Same call shape as SimulEval's ``DifferentiableAverageLagging`` (the entry of
+    ``LATENCY_METRICS`` the reference's criteria use); one kernel launch forward, one backward."""
+    return DALFunction.apply(delays, src_lens, ref_lens, target_padding_mask)

@@ -27,12 +27,24 @@ def _last_dim_op(tensor, dim, fn):
     return fn(moved).transpose(dim, nd - 1)
 
 
+def _checked_cumprod(tensor, dim, eps, inclusive):
+    """The reference reads ``(tensor + eps < 0).any().item()`` on every call (functions.py:57):
+    same single host read here, on a status word of this call's own, so bits left by unrelated
+    operators on the shared per-device word are neither consumed nor reported here."""
+    word = torch.zeros(1, dtype=torch.int32, device=tensor.device)
+    out = _last_dim_op(tensor, dim, lambda x: ops.exclusive_cumprod_lastdim(x, eps, inclusive=inclusive,
+                                                                            status=word))
+    bits = int(word.item())
+    if bits:
+        _lib.raise_for_status(bits)
+    return out
+
+
 def safe_cumprod(tensor, dim: int, eps: float = 1e-10):
     """functions.py:48-66: exp(cumsum(log(tensor + eps))) along `dim`; RuntimeError on
-    tensor + eps < 0 (checked with a host read, as the reference's ``.item()`` does)."""
-    out = _last_dim_op(tensor, dim, lambda x: ops.exclusive_cumprod_lastdim(x, eps, inclusive=True))
-    _lib.check_status(tensor.device)
-    return out
+    tensor + eps < 0.  Differentiable, like the reference's composition."""
+    _lib.require_cuda(tensor)
+    return _checked_cumprod(tensor, dim, eps, True)
 
 
 def exclusive_cumprod(tensor, dim: int, eps: float = 1e-10):
@@ -41,9 +53,8 @@ def exclusive_cumprod(tensor, dim: int, eps: float = 1e-10):
         raise RuntimeError(
             "Cumprod on dimension 3 and more is not implemented"
         )
-    out = _last_dim_op(tensor, dim, lambda x: ops.exclusive_cumprod_lastdim(x, eps))
-    _lib.check_status(tensor.device)       # safe_cumprod's `.item()` check (functions.py:57)
-    return out
+    _lib.require_cuda(tensor)
+    return _checked_cumprod(tensor, dim, eps, False)
 
 
 def moving_sum(x, start_idx: int, end_idx: int):

@@ -15,35 +15,27 @@ def waitk_p_choose(
     key_padding_mask: Optional[Tensor] = None,
     incremental_state: Optional[Dict[str, Dict[str, Optional[Tensor]]]] = None
 ):
-    """p_choose_strategy.py:6-53: one-hot diagonal j == min(i + k - 1, eos).  Integer index
-    generation only (no kernel needed).  Like the reference it dereferences
-    ``incremental_state`` unconditionally (:35) -- wait-k *training* without an incremental
-    state is broken upstream and is left so."""
-    if key_padding_mask is not None:
-        key_eos = (~key_padding_mask).long().sum(-1) - 1
-    else:
-        key_eos = torch.full((bsz,), src_len - 1)
-    monotonic_step = (
-        torch.arange(tgt_len, device=key_eos.device)
-        .add(waitk_lagging - 1)
-        .unsqueeze(0)
-        .expand(bsz, -1)
-        .clone()
-    )
+    """p_choose_strategy.py:6-53 -- wait-k policy: target step i writes after reading source
+    frame ``min(i + k - 1, eos)`` (no ``min`` when ``incremental_state["online"]``).
+
+    Same signature, result (bool ``[bsz, 1, src_len]``, device of the mask -- CPU without one,
+    :25) and failure mode as the reference: ``incremental_state`` is dereferenced
+    unconditionally (:35), so calling it without one (wait-k *training*) raises AttributeError
+    upstream and does so here -- SURVEY Appendix Q; not silently "fixed".  Because that makes the
+    reference's final ``[:, -1:]`` slice (:50-51) unconditional too, only the LAST target row is
+    ever returned, and only that row is generated here: one comparison of ``arange(src_len)``
+    against a ``[bsz, 1]`` step index instead of a ``[bsz, tgt_len, src_len]`` one-hot.
+    Integer index generation on ``bsz * src_len`` elements: not a kernel."""
     online = incremental_state.get("online", False)
+    if key_padding_mask is None:
+        last_frame = torch.full((bsz,), src_len - 1)
+    else:
+        last_frame = key_padding_mask.logical_not().long().sum(-1) - 1
+    dev = last_frame.device
+    step = torch.full((bsz, 1), tgt_len - 1 + waitk_lagging - 1, dtype=torch.long, device=dev)
     if not online:
-        monotonic_step = monotonic_step.clip(
-            max=key_eos.unsqueeze(1).expand(-1, tgt_len)
-        )
-    p_choose = (
-        torch.arange(src_len, device=key_eos.device)
-        .unsqueeze(0)
-        .unsqueeze(1)
-        .expand(bsz, tgt_len, -1)
-    ) == monotonic_step.unsqueeze(2)
-    if incremental_state is not None:
-        p_choose = p_choose[:, -1:]
-    return p_choose
+        step = torch.minimum(step, last_frame.view(bsz, 1))
+    return (torch.arange(src_len, device=dev).view(1, 1, src_len) == step.view(bsz, 1, 1))
 
 
 def learnable_p_choose(

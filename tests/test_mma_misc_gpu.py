@@ -177,3 +177,38 @@ def test_module_mixin_train_and_infer_against_oracle():
     assert torch.equal(host2.state["head_read"].cpu().view(-1), hr)
     assert torch.equal(alpha1.cpu(), a1)
     torch.testing.assert_close(beta1.cpu(), b1, rtol=1e-5, atol=1e-7)
+
+
+def test_moving_sum_and_cumprod_are_differentiable():
+    """the reference's moving_sum (conv1d) and exclusive/safe_cumprod (log-cumsum-exp)
+    are differentiable; the mirrors must not drop the graph."""
+    from simulst_b200.utils.functions import exclusive_cumprod, moving_sum, safe_cumprod
+    g = torch.Generator().manual_seed(6)
+    x = torch.rand(2, 3, 41, generator=g) * 0.9 + 0.05
+    w = torch.randn(2, 3, 41, generator=g)
+    for fn_k, fn_o in ((lambda t: moving_sum(t, 4, 2), lambda t: omma.moving_sum(t, 4, 2)),
+                       (lambda t: moving_sum(t, 1, 5), lambda t: omma.moving_sum(t, 1, 5)),
+                       (lambda t: exclusive_cumprod(t, dim=2, eps=1e-6), lambda t: omma.exclusive_cumprod(t, 2, 1e-6)),
+                       (lambda t: safe_cumprod(t, dim=2, eps=1e-6), lambda t: omma.safe_cumprod(t, 2, 1e-6)),
+                       (lambda t: exclusive_cumprod(t, dim=1, eps=1e-6), lambda t: omma.exclusive_cumprod(t, 1, 1e-6))):
+        x_k = x.to(DEV).requires_grad_()
+        x_o = x.clone().requires_grad_()
+        y_k = fn_k(x_k)
+        assert y_k.grad_fn is not None
+        (y_k * w.to(DEV)).sum().backward()
+        (fn_o(x_o) * w).sum().backward()
+        assert_parity(x_k.grad, x_o.grad, "grad", atol=2e-6)
+
+
+def test_cumprod_check_ignores_stale_status_bits():
+    """safe_cumprod's negative-input check uses a status word of its own."""
+    import simulst_b200
+    from simulst_b200 import ops
+    from simulst_b200.utils.functions import safe_cumprod
+    bad = torch.rand(1, 2, 16, device=DEV)
+    bad[0, 0, 3] = 1.5
+    ops.mma_train(bad, None, None, mass_preservation=False)        # leaves ST_RANGE on the device word
+    out = safe_cumprod(torch.rand(1, 1, 8, device=DEV), dim=2)     # must not raise for it
+    assert out.shape == (1, 1, 8)
+    with pytest.raises(AssertionError, match="Incorrect values"):
+        simulst_b200.check_status(torch.device(DEV))

@@ -1,0 +1,42 @@
+"""CPU: oracle restatements and torch-only host mirrors against the round-2 golden vectors
+(tests/golden/make_golden_r2.py, generated from the unmodified reference)."""
+import pytest
+import torch
+
+from oracle import mma as omma
+from tests.golden_io import load, opt
+
+WAITK = load("waitk.npz")
+LEFT = load("mma_leftpad.npz")
+
+
+@pytest.mark.parametrize("name", list(WAITK))
+def test_waitk_p_choose_mirror_and_oracle_match_golden(name):
+    """a11: the mirror generates only the last target row (the reference's unconditional
+    ``[:, -1:]``); result, dtype and shape must equal the reference's."""
+    from simulst_b200.utils.p_choose_strategy import waitk_p_choose
+    c = WAITK[name]
+    t, s, b, k, masked, online = [int(v) for v in c.cfg]
+    inc = {"online": True} if online else {}
+    got = waitk_p_choose(t, s, b, k, opt(c.mask), inc)
+    assert got.dtype == torch.bool and tuple(got.shape) == tuple(c.p_choose.shape) == (b, 1, s)
+    assert torch.equal(got, c.p_choose)
+    ora = omma.waitk_p_choose(t, s, b, k, opt(c.mask), online=bool(online), last_only=True)
+    assert torch.equal(ora, c.p_choose)
+
+
+def test_waitk_p_choose_without_incremental_state_raises_like_upstream():
+    """p_choose_strategy.py:35 dereferences incremental_state unconditionally."""
+    from simulst_b200.utils.p_choose_strategy import waitk_p_choose
+    with pytest.raises(AttributeError):
+        waitk_p_choose(3, 4, 1, 1, None, None)
+
+
+def test_left_padding_oracle_matches_golden():
+    c = LEFT["left"]
+    p = c.p.clone().requires_grad_()
+    a = omma.expected_alignment_from_p_choose(p, c.mask, eps=1e-6)
+    a = omma.mass_preservation(a, c.mask, left_padding=True)
+    (a * c.g_alpha).sum().backward()
+    torch.testing.assert_close(a, c.alpha, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(p.grad, c.grad_p, rtol=1e-5, atol=1e-6)
