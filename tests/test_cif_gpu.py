@@ -156,7 +156,8 @@ def test_cif_layer_forward_and_chunked_infer():
     tl = torch.tensor([20, 15, 11])
     ref = ocif.cif_layer_forward(x, a, beta, mask, tl)
     got = cif_layer_forward(x.to(DEV), a.to(DEV), beta, beta / 2, mask.to(DEV), tl.to(DEV))
-    assert_parity(got["cif_out"][0].cpu(), ref["cif_out"][0], "cif_out")
+    feat = cif_tols(x, beta, int(tl.max()), s)["feat"]
+    assert_parity(got["cif_out"][0].cpu(), ref["cif_out"][0], "cif_out", extra_atol=feat)
     assert torch.equal(got["cif_lengths"][0].cpu(), ref["cif_lengths"][0])
     # streaming: 6 chunks of 15 frames, one utterance
     st_ref, st_got = {}, {}
@@ -168,10 +169,10 @@ def test_cif_layer_forward_and_chunked_infer():
         o = cif_layer_infer(x1[sl].to(DEV), a1[:, sl].to(DEV), st_got, beta, beta / 2, finish=fin)
         assert int(o["cif_lengths"][0]) == int(r["cif_lengths"][0])
         if r["cif_out"][0].numel():
-            assert_parity(o["cif_out"][0].cpu(), r["cif_out"][0], f"chunk{k}")
+            assert_parity(o["cif_out"][0].cpu(), r["cif_out"][0], f"chunk{k}", extra_atol=feat)
         if not fin:
-            assert_parity(st_got["prev_weight"].cpu(), st_ref["prev_weight"], "prev_weight")
-            assert_parity(st_got["prev_feat"].cpu(), st_ref["prev_feat"], "prev_feat")
+            assert_parity(st_got["prev_weight"].cpu(), st_ref["prev_weight"], "prev_weight", extra_atol=4 * ULP * 16)
+            assert_parity(st_got["prev_feat"].cpu(), st_ref["prev_feat"], "prev_feat", extra_atol=feat)
 
 
 def test_cif_bf16_input_close_to_fp32_oracle():

@@ -131,8 +131,10 @@ def test_mma_train_matches_oracle(n, t, s, masked, chunk, cfg, kernel_family):
     a64, b64 = a64.detach(), b64.detach()
     assert_parity(alpha, a_o.detach(), "alpha", a64)
     assert_parity(beta, b_o.detach(), "beta", b64)
-    assert_parity(gp, p_o.grad, "grad_p", p64.grad)
-    assert_parity(ge, se_o.grad, "grad_soft_energy", se64.grad)
+    # gradients are length-S sums of upstream-gradient-sized terms: rounding floor 2*2^-24*sqrt(S)*|g|
+    floor = 2.0 * 2.0 ** -24 * s ** 0.5 * max(float(ga.abs().max()), float(gb.abs().max()))
+    assert_parity(gp, p_o.grad, "grad_p", p64.grad, extra_atol=floor)
+    assert_parity(ge, se_o.grad, "grad_soft_energy", se64.grad, extra_atol=floor)
     # accuracy against the fp64 restatement: not worse than 2x the reference's own error
     err_k = (alpha.double() - a64).abs().max().item()
     err_r = (a_o.detach().double() - a64).abs().max().item()

@@ -19,6 +19,18 @@ pytestmark = [pytest.mark.gpu, pytest.mark.reference]
 DEV = "cuda"
 
 
+@pytest.fixture(autouse=True)
+def _ieee_fp32_around_the_hot_path():
+    """The projections / convolutions AROUND the hot path run in cuBLAS / cuDNN here and in MKL on
+    the CPU side; TF32 (cuDNN's default for convolutions) would put 1e-3 relative noise into the
+    inputs of the path under test."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def _pair(kind, how, mass_preservation=True, heads=4, embed=64, seed=3):
     """(reference module on CPU, same weights on the GPU with the kernel-backed method bodies)."""
     from simulst_b200.modules.monotonic_multihead_attention import (
@@ -76,11 +88,14 @@ def test_reference_forward_training_pass(kind, how, masked):
     assert_parity(out_m, out_r.detach(), f"{kind}/{how} attn", **kw)
     assert_parity(q_m.grad, q_r.grad, "grad query", rtol=1e-4, atol=2e-5)
     assert_parity(k_m.grad, k_r.grad, "grad key", rtol=1e-4, atol=2e-5)
+    # some parameter gradients are analytically zero (a key bias shifts every energy of a query
+    # alike): both sides hold rounding noise there, so the floor is tied to the largest gradient
+    g_scale = max(float(p.grad.abs().max()) for p in ref.parameters() if p.grad is not None)
     for (name, p_r), (_, p_m) in zip(ref.named_parameters(), mine.named_parameters()):
         if p_r.grad is None:
             assert p_m.grad is None, name
             continue
-        assert_parity(p_m.grad, p_r.grad, f"grad {name}", rtol=1e-4, atol=2e-5)
+        assert_parity(p_m.grad, p_r.grad, f"grad {name}", rtol=1e-4, atol=2e-5, extra_atol=2e-6 * g_scale)
 
 
 @pytest.mark.parametrize("kind", ["infinite_lookback", "hard_aligned"])
@@ -171,10 +186,9 @@ def test_cif_layer_mixin_on_reference_class_forward(sg_alpha, masked):
     assert_parity(out_m["alpha"][0], out_r["alpha"][0].detach(), "alpha", atol=5e-6)
     assert_parity(x_m.grad, x_r.grad, "grad x", rtol=1e-4, atol=1e-4)
     for (name, p_r), (_, p_m) in zip(ref.named_parameters(), mine.named_parameters()):
-        if sg_alpha:
-            assert p_r.grad is None and p_m.grad is None, name       # stop-gradient on the weight branch
-        else:
-            assert_parity(p_m.grad, p_r.grad, f"grad {name}", rtol=1e-4, atol=1e-4)
+        # (sg_alpha only detaches x on its way INTO alpha_proj: the projection's own parameters
+        # still receive the CIF gradient through alpha)
+        assert_parity(p_m.grad, p_r.grad, f"grad {name}", rtol=1e-4, atol=1e-4)
 
 
 def test_cif_layer_mixin_on_reference_class_streaming():
