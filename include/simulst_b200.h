@@ -200,6 +200,51 @@ int simulst_dal_bwd(const float* delays, const int64_t* src_lens, const int64_t*
                     float* grad_delays, int N, int T, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * SSNT lattice loss.  Replaces ssnt_loss / ssnt_loss_mem
+ * (codebase/criterion/ssnt_loss/ssnt_loss.py:45-151 / :154-271): the MMA recurrence in log space
+ * with the word-prediction log-probability folded in,
+ *     log_alpha[i+1] = clamp(trans[i] + log_p[i] + lcp[i]
+ *                            + logcumsumexp(log1p(lambda) + log_alpha[i] - lcp[i]), neg_inf, 0).
+ * One CTA per sample, lattice row on chip, scans over the source axis; backward recomputes them.
+ *
+ *   log_probs        [rows, S, V] lp_dtype  word log-probs (log_softmax output); rows = N*T in the
+ *                                           padded layout, T_flat (targets concatenated) in the flat one
+ *   targets          [rows] int64
+ *   emit             [rows, S] e_dtype      emission logits (emit_is_logits != 0) or probabilities
+ *   source_lengths, target_lengths [N] int64
+ *   row_offsets      [N] int64   flat layout: first row of sample n (exclusive cumsum of target_lengths);
+ *                                NULL selects the padded layout (sample n owns rows n*T .. n*T+T-1)
+ *   lattice_offsets  [N] int64   flat layout: row of sample n's alpha_0 in `lattice`
+ *                                (exclusive cumsum of target_lengths + 1); NULL in the padded layout
+ *   lattice          fp32 out    padded: [N, T, S] = log_alpha[:, 1:]; flat: [T_flat + N, S] incl. alpha_0 rows
+ *   log_p_choose     [rows, S] fp32 out  log p with source padding filled with neg_inf (may be NULL)
+ *   loss             [N] fp32 out        -log_alpha[n, target_len, source_len - 1] (reduction: caller)
+ * S <= SIMULST_SSNT_MAX_SRC.  NaN in the lattice sets SIMULST_ST_NAN in `status`. */
+#define SIMULST_SSNT_MAX_SRC 4096
+int simulst_ssnt_fwd(const void* log_probs, int lp_dtype, const int64_t* targets,
+                     const void* emit, int e_dtype, int emit_is_logits,
+                     const int64_t* source_lengths, const int64_t* target_lengths,
+                     const int64_t* row_offsets, const int64_t* lattice_offsets,
+                     float* lattice, float* log_p_choose, float* loss,
+                     int N, int T, int S, int V, float neg_inf, float fastemit_lambda,
+                     unsigned* status, void* stream);
+/* Backward.  grad_loss [N]; grad_lattice (layout of lattice) and grad_log_p_choose [rows, S] may be
+ * NULL.  grad_emit [rows, S] e_dtype out.  grad_log_probs [rows, S, V] lp_dtype must be ZERO-FILLED
+ * by the caller (NULL: not wanted): the kernel writes the one gathered column per (row, frame). */
+int simulst_ssnt_bwd(const void* log_probs, int lp_dtype, const int64_t* targets,
+                     const void* emit, int e_dtype, int emit_is_logits,
+                     const int64_t* source_lengths, const int64_t* target_lengths,
+                     const int64_t* row_offsets, const int64_t* lattice_offsets,
+                     const float* lattice, const float* grad_loss, const float* grad_lattice,
+                     const float* grad_log_p_choose, void* grad_emit, void* grad_log_probs,
+                     int N, int T, int S, int V, float neg_inf, float fastemit_lambda, void* stream);
+/* prob_check(log_probs, neg_inf, logp=True) (ssnt_loss.py:29-42, called at :80 and :200): NaN ->
+ * SIMULST_ST_NAN, value > 0 or < neg_inf -> SIMULST_ST_RANGE, OR-ed into `status`; one streaming
+ * pass over the tensor (16-byte aligned pointer). */
+int simulst_logprob_check(const void* log_probs, int dtype, long long numel, float neg_inf,
+                          unsigned* status, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Stand-alone pieces (same math, rows independent): used when the reference functions are
  * called one by one rather than through monotonic_attention_process_train.
  */

@@ -24,6 +24,7 @@ MMA_ENERGY_F16_FILL = 4
 MMA_LEFT_PADDING = 8
 MMA_RIGHT_PADDING = 16
 MMA_MAX_SRC = 16384
+SSNT_MAX_SRC = 4096
 SOFT_ATTENTION_MAX_SRC = 9600      # stand-alone soft attention: 6 fp32 rows + scratch in 227 KB
 
 _lib = None
@@ -60,6 +61,13 @@ SIGNATURES = {
     "simulst_dal_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "simulst_dal_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                 c_void_p]),
+    "simulst_ssnt_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
+    "simulst_ssnt_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
+    "simulst_logprob_check": (c_int, [c_void_p, c_int, c_longlong, c_float, c_void_p, c_void_p]),
     "simulst_soft_attention_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                            c_int, c_int, c_int, c_float, c_int, c_uint,
                                            c_void_p, c_void_p]),

@@ -523,3 +523,89 @@ def differentiable_average_lagging(delays: Tensor, src_lens: Tensor, ref_lens: O
     """Same call shape as SimulEval's ``DifferentiableAverageLagging`` (the entry of
     ``LATENCY_METRICS`` the reference's criteria use); one kernel launch forward, one backward."""
     return DALFunction.apply(delays, src_lens, ref_lens, target_padding_mask)
+
+
+# ----------------------------------------------------------------------------- SSNT lattice loss
+class SSNTFunction(torch.autograd.Function):
+    """ssnt_loss / ssnt_loss_mem (reference codebase/criterion/ssnt_loss/ssnt_loss.py:45-271) up
+    to the reduction: (log_probs, emit) -> (loss [N], lattice, log_p_choose).  One forward and one
+    backward launch; the backward recomputes the scans from the saved lattice."""
+
+    @staticmethod
+    def forward(ctx, log_probs, emit, targets, source_lengths, target_lengths, emit_is_logits,
+                neg_inf, fastemit_lambda, flat):
+        lib = _lib.load()
+        dev = _lib.require_cuda(log_probs, emit, targets, source_lengths, target_lengths)
+        n = source_lengths.numel()
+        lp = log_probs.contiguous()
+        em = emit.contiguous()
+        tg = targets.contiguous().long()
+        src = source_lengths.contiguous().long()
+        tgt = target_lengths.contiguous().long()
+        if flat:
+            rows, s = em.shape
+            t = 0
+            row_off = (torch.cumsum(tgt, 0) - tgt).contiguous()
+            lat_off = (torch.cumsum(tgt + 1, 0) - (tgt + 1)).contiguous()
+            lattice = torch.empty((rows + n, s), dtype=torch.float32, device=dev)
+        else:
+            n_e, t, s = em.shape
+            if n_e != n:
+                raise ValueError(f"emit has batch {n_e}, lengths have {n}")
+            rows = n * t
+            row_off = lat_off = None
+            lattice = torch.empty((n, t, s), dtype=torch.float32, device=dev)
+        v = lp.shape[-1]
+        if lp.numel() != rows * s * v or tg.numel() != rows:
+            raise ValueError("log_probs / targets do not match the emission tensor")
+        if s > _lib.SSNT_MAX_SRC:
+            raise ValueError(f"src_len {s} exceeds the on-chip row limit {_lib.SSNT_MAX_SRC}")
+        log_p = torch.empty(em.shape, dtype=torch.float32, device=dev)
+        loss = torch.empty(n, dtype=torch.float32, device=dev)
+        status = _lib.status_word(dev)
+        with torch.cuda.device(dev):
+            rc = lib.simulst_ssnt_fwd(_lib.ptr(lp), _lib.dtype_enum(lp.dtype), _lib.ptr(tg), _lib.ptr(em),
+                                      _lib.dtype_enum(em.dtype), 1 if emit_is_logits else 0, _lib.ptr(src),
+                                      _lib.ptr(tgt), _lib.ptr(row_off), _lib.ptr(lat_off), _lib.ptr(lattice),
+                                      _lib.ptr(log_p), _lib.ptr(loss), n, t, s, v, float(neg_inf),
+                                      float(fastemit_lambda), _lib.ptr(status), _lib.stream_ptr(dev))
+        _lib.check(rc, "simulst_ssnt_fwd")
+        ctx.save_for_backward(lp, em, tg, src, tgt, row_off, lat_off, lattice)
+        ctx.cfg = (n, t, s, v, bool(emit_is_logits), float(neg_inf), float(fastemit_lambda))
+        ctx.set_materialize_grads(False)
+        return loss, lattice, log_p
+
+    @staticmethod
+    def backward(ctx, g_loss, g_lattice, g_log_p):
+        lib = _lib.load()
+        lp, em, tg, src, tgt, row_off, lat_off, lattice = ctx.saved_tensors
+        n, t, s, v, is_logits, neg_inf, lam = ctx.cfg
+        dev = em.device
+        gl = (g_loss.contiguous().float() if g_loss is not None
+              else torch.zeros(n, dtype=torch.float32, device=dev))
+        glat = g_lattice.contiguous().float() if g_lattice is not None else None
+        glp = g_log_p.contiguous().float() if g_log_p is not None else None
+        g_emit = torch.empty_like(em)
+        # the gather's adjoint is a scatter into zeros, as in autograd; only when someone wants it
+        g_probs = torch.zeros_like(lp) if ctx.needs_input_grad[0] else None
+        with torch.cuda.device(dev):
+            rc = lib.simulst_ssnt_bwd(_lib.ptr(lp), _lib.dtype_enum(lp.dtype), _lib.ptr(tg), _lib.ptr(em),
+                                      _lib.dtype_enum(em.dtype), 1 if is_logits else 0, _lib.ptr(src),
+                                      _lib.ptr(tgt), _lib.ptr(row_off), _lib.ptr(lat_off), _lib.ptr(lattice),
+                                      _lib.ptr(gl), _lib.ptr(glat), _lib.ptr(glp), _lib.ptr(g_emit),
+                                      _lib.ptr(g_probs), n, t, s, v, neg_inf, lam, _lib.stream_ptr(dev))
+        _lib.check(rc, "simulst_ssnt_bwd")
+        return g_probs, g_emit, None, None, None, None, None, None, None
+
+
+def logprob_check(log_probs: Tensor, neg_inf: float = -1e8):
+    """prob_check(tensor, neg_inf=..., logp=True) of the reference (ssnt_loss.py:29-42) as one
+    streaming pass into the device status word (raise via check_status / strict mode)."""
+    lib = _lib.load()
+    dev = _lib.require_cuda(log_probs)
+    x = log_probs.contiguous()
+    with torch.cuda.device(dev):
+        rc = lib.simulst_logprob_check(_lib.ptr(x), _lib.dtype_enum(x.dtype), x.numel(), float(neg_inf),
+                                       _lib.ptr(_lib.status_word(dev)), _lib.stream_ptr(dev))
+    _lib.check(rc, "simulst_logprob_check")
+    _lib.maybe_check(dev)

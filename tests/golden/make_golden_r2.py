@@ -150,7 +150,71 @@ def gen_leftpad():
     return _save("mma_leftpad.npz", out, names)
 
 
-GENERATORS = [("waitk", gen_waitk), ("latency", gen_latency), ("mma_leftpad", gen_leftpad)]
+# ----------------------------------------------------------------------------- SSNT
+SSNT_CASES = [
+    # name, N, T, S, V, use_logits, ragged, fastemit_lambda, reduction
+    ("logits_full",   3, 5, 20, 7,  True,  False, 0.0,  "none"),
+    ("probs_full",    3, 5, 20, 7,  False, False, 0.0,  "none"),
+    ("logits_ragged", 4, 7, 33, 11, True,  True,  0.0,  "sum"),
+    ("probs_ragged",  4, 7, 33, 11, False, True,  0.0,  "mean"),
+    ("fastemit",      2, 6, 40, 5,  True,  True,  0.01, "sum"),
+    ("long",          2, 24, 150, 9, True, True,  0.0,  "sum"),
+    ("one",           1, 1, 1, 3,   True,  False, 0.0,  "none"),
+]
+
+
+def gen_ssnt():
+    ref = ref_loader.load_ssnt()
+    out, names = {}, []
+    for idx, (name, n, t, s, v, use_logits, ragged, lam, red) in enumerate(SSNT_CASES):
+        g = torch.Generator().manual_seed(6000 + idx)
+        logits = torch.randn(n, t, s, v, generator=g).requires_grad_()
+        emit = (torch.randn(n, t, s, generator=g) - 1.0)
+        targets = torch.randint(0, v, (n, t), generator=g)
+        if ragged:
+            src_len = torch.randint(max(1, s // 2), s + 1, (n,), generator=g)
+            tgt_len = torch.randint(max(1, t // 2), t + 1, (n,), generator=g)
+            src_len[0], tgt_len[0] = s, t
+        else:
+            src_len, tgt_len = torch.full((n,), s), torch.full((n,), t)
+        if use_logits:
+            emit_in = emit.clone().requires_grad_()
+            kw = {"emit_logits": emit_in}
+        else:
+            emit_in = torch.sigmoid(emit).clone().requires_grad_()
+            kw = {"emit_probs": emit_in}
+        lp = logits.log_softmax(-1)
+        loss, lattice, log_p = ref.ssnt_loss(lp, targets, src_len, tgt_len, reduction=red,
+                                             fastemit_lambda=lam, **kw)
+        w = torch.randn(loss.shape, generator=g) if loss.dim() else torch.tensor(1.0)
+        (loss * w).sum().backward()
+        # the memory-efficient variant on the same sample (targets concatenated)
+        keep = torch.arange(t)[None, :] < tgt_len[:, None]
+        kw_m = {k: (x.detach()[keep]) for k, x in kw.items()}
+        loss_m, lattice_m, _ = ref.ssnt_loss_mem(lp.detach()[keep], targets[keep], src_len, tgt_len,
+                                                 reduction=red, fastemit_lambda=lam, **kw_m)
+        names.append(name)
+        out[f"{name}/cfg"] = np.array([n, t, s, v, int(use_logits)], np.int64)
+        out[f"{name}/fastemit"] = np.array(lam, np.float64)
+        out[f"{name}/reduction"] = np.array(red)
+        out[f"{name}/logits"] = _np(logits)
+        out[f"{name}/emit"] = _np(emit_in)
+        out[f"{name}/targets"] = _np(targets)
+        out[f"{name}/source_lengths"] = _np(src_len)
+        out[f"{name}/target_lengths"] = _np(tgt_len)
+        out[f"{name}/w"] = _np(w)
+        out[f"{name}/loss"] = _np(loss)
+        out[f"{name}/lattice"] = _np(lattice)
+        out[f"{name}/log_p_choose"] = _np(log_p)
+        out[f"{name}/grad_logits"] = _np(logits.grad)
+        out[f"{name}/grad_emit"] = _np(emit_in.grad)
+        out[f"{name}/loss_mem"] = _np(loss_m)
+        out[f"{name}/lattice_mem"] = _np(lattice_m)
+    return _save("ssnt.npz", out, names)
+
+
+GENERATORS = [("waitk", gen_waitk), ("latency", gen_latency), ("mma_leftpad", gen_leftpad),
+              ("ssnt", gen_ssnt)]
 
 
 if __name__ == "__main__":
