@@ -245,6 +245,31 @@ int simulst_logprob_check(const void* log_probs, int dtype, long long numel, flo
                           unsigned* status, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * CTC best alignment.  Replaces the reference's only native kernel and the
+ * Python around it, in one launch:
+ *   ctc_alignment_log_alpha_gpu_kernel   codebase/criterion/best_alignment/best_alignment.cu:58-202
+ *   best_alignment(...)                  codebase/criterion/best_alignment/__init__.py:25-111
+ *                                        (final-state choice, S-iteration back-trace, labels)
+ *   log_probs       [S, N, V] dtype   log emission probabilities (after log_softmax), time-major
+ *   targets         [N, target_stride] int64, target_stride >= Tmax
+ *   input_lengths, target_lengths [N] int64  (device pointers: the reference copies them to the
+ *                                     host and back, best_alignment.cpp:16-23)
+ *   workspace       simulst_ctc_workspace_bytes(N, S, Tmax) bytes: one BYTE per (sample, frame,
+ *                   state) holding the arg-max jump 0/1/2 (the reference stores int64 indices and a
+ *                   fp32 log_alpha of the same shape)
+ *   nll             [N] fp32 out, may be NULL   -log(sum of the two final states), .cu:187-201
+ *   states          [N, S] int64 out   state sequence in [0, 2T+1); 0 for frames >= input_length
+ *   labels          [N, S] int64 out, may be NULL   states translated to labels (as_labels=True)
+ * 2*Tmax+1 <= 4096.  No host read: CUDA-graph capturable. */
+long long simulst_ctc_workspace_bytes(int N, int S, int Tmax);
+int simulst_ctc_best_alignment(const void* log_probs, int dtype,
+                               const int64_t* targets, int target_stride,
+                               const int64_t* input_lengths, const int64_t* target_lengths,
+                               int blank, uint8_t* workspace, float* nll,
+                               int64_t* states, int64_t* labels,
+                               int N, int S, int V, int Tmax, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Stand-alone pieces (same math, rows independent): used when the reference functions are
  * called one by one rather than through monotonic_attention_process_train.
  */

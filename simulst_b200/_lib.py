@@ -68,6 +68,10 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "simulst_logprob_check": (c_int, [c_void_p, c_int, c_longlong, c_float, c_void_p, c_void_p]),
+    "simulst_ctc_workspace_bytes": (c_longlong, [c_int, c_int, c_int]),
+    "simulst_ctc_best_alignment": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                           c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_int, c_int, c_int, c_int, c_void_p]),
     "simulst_soft_attention_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                            c_int, c_int, c_int, c_float, c_int, c_uint,
                                            c_void_p, c_void_p]),

@@ -609,3 +609,38 @@ def logprob_check(log_probs: Tensor, neg_inf: float = -1e8):
                                        _lib.ptr(_lib.status_word(dev)), _lib.stream_ptr(dev))
     _lib.check(rc, "simulst_logprob_check")
     _lib.maybe_check(dev)
+
+
+# ----------------------------------------------------------------------------- CTC best alignment
+def ctc_best_alignment(log_prob: Tensor, targets: Tensor, input_lengths: Tensor, target_lengths: Tensor,
+                       blank: int = 0, as_labels: bool = False, max_target_length: Optional[int] = None,
+                       return_nll: bool = False):
+    """Viterbi forward + back-trace in one launch (reference
+    codebase/criterion/best_alignment/{best_alignment.cu:58-202, __init__.py:25-111}).
+    log_prob (S, N, V); targets (N, T); lengths (N,) on the device.  `max_target_length`: the
+    width of the state row (2*max+1); defaults to targets.size(1) -- no host read of the lengths
+    (the reference copies both length vectors to the host on every call)."""
+    lib = _lib.load()
+    dev = _lib.require_cuda(log_prob, targets, input_lengths, target_lengths)
+    if log_prob.dim() != 3 or targets.dim() != 2:
+        raise ValueError("log_prob must be (S, N, V) and targets (N, T)")
+    s, n, v = log_prob.shape
+    lp = log_prob.contiguous()
+    tg = targets.contiguous().long()
+    il = input_lengths.contiguous().long()
+    tl = target_lengths.contiguous().long()
+    t_max = int(max_target_length) if max_target_length is not None else tg.shape[1]
+    if t_max > tg.shape[1]:
+        raise ValueError("max_target_length exceeds targets.size(1)")
+    ws = torch.empty(max(int(lib.simulst_ctc_workspace_bytes(n, s, t_max)), 1), dtype=torch.uint8, device=dev)
+    states = torch.empty((n, s), dtype=torch.int64, device=dev)
+    labels = torch.empty((n, s), dtype=torch.int64, device=dev) if as_labels else None
+    nll = torch.empty(n, dtype=torch.float32, device=dev) if return_nll else None
+    with torch.cuda.device(dev):
+        rc = lib.simulst_ctc_best_alignment(_lib.ptr(lp), _lib.dtype_enum(lp.dtype), _lib.ptr(tg), tg.shape[1],
+                                            _lib.ptr(il), _lib.ptr(tl), int(blank), _lib.ptr(ws), _lib.ptr(nll),
+                                            _lib.ptr(states), _lib.ptr(labels), n, s, v, t_max,
+                                            _lib.stream_ptr(dev))
+    _lib.check(rc, "simulst_ctc_best_alignment")
+    out = labels if as_labels else states
+    return (out, nll) if return_nll else out
