@@ -179,6 +179,51 @@ int simulst_mma_train_bwd_delays(const void* p_choose, int p_dtype,
                                  void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Pooled p_choose producer: the MMA training path of the fixed pre-decision
+ * wrappers.  Replaces FixedStrideMonotonicAttention.insert_zeros and the tail of its p_choose()
+ * (codebase/modules/fixed_pre_decision.py:85-95 and :139-159) fused with the three functions of
+ * simulst_mma_train_fwd: the caller hands over p_choose_pooled [N,T,Sp], Sp = ceil(S / ratio),
+ * as produced by p_choose_from_qk on the pooled keys (:133-138), instead of the dense [N,T,S]
+ * tensor in which only every ratio-th column (and column S-1) is non-zero:
+ *     dense[n,t,j] = pooled[n,t,(j+1)/ratio - 1]   if (j+1) % ratio == 0
+ *                  = pooled[n,t,Sp-1]              if j == S-1     (:156-159)
+ *                  = 0                             otherwise
+ * The kernels form that row in registers (1/ratio of the p_choose bytes are read, none staged)
+ * when simulst_mma_pooled_is_fused() says so: hard or infinite-lookback attention, ratio >= the
+ * per-thread element count (8; 4 for S <= 128), S <= 4096, S*esize a multiple of 16 bytes, and
+ * either no padding mask or the SIMULST_MMA_RIGHT_PADDING promise (forward() asserts right padding,
+ * monotonic_multihead_attention.py:378-381; the kernel verifies the promise).  Every other shape
+ * is served by expanding into `p_dense` and running the dense kernels, bit-identical results.
+ *
+ *   p_pooled       [N,T,Sp] p_dtype
+ *   p_dense        [N,T,S]  p_dtype out   the zero-upsampled p_choose the reference's
+ *                                         process_train returns; optional (NULL) when the call is
+ *                                         fused, required otherwise (it is then also the workspace)
+ *   grad_p_pooled  [N,T,Sp] gp_dtype out  gradient w.r.t. p_pooled (each pooled element owns one
+ *                                         dense column, so this is a gather of the dense gradient)
+ *   grad_p_dense   [N,T,S]  workspace     required (with p_dense) when the call is not fused
+ * All other arguments as in simulst_mma_train_{fwd,bwd}_delays. */
+int simulst_mma_pooled_is_fused(int p_dtype, int S, int ratio, int chunk_size, unsigned flags, int has_mask);
+int simulst_mma_train_fwd_pooled(const void* p_pooled, int p_dtype, int ratio,
+                                 const void* soft_energy, int e_dtype,
+                                 const uint8_t* padding_mask, void* p_dense,
+                                 float* alpha, float* beta, float* side, float* expected_delays,
+                                 int N, int T, int S,
+                                 float eps, int chunk_size, unsigned flags,
+                                 unsigned* status, void* stream);
+int simulst_mma_train_bwd_pooled(const void* p_pooled, int p_dtype, int ratio,
+                                 const void* soft_energy, int e_dtype,
+                                 const uint8_t* padding_mask, const void* p_dense,
+                                 const float* alpha, const float* side,
+                                 const float* grad_alpha, const float* grad_beta,
+                                 const float* grad_expected_delays,
+                                 void* grad_p_pooled, int gp_dtype, void* grad_p_dense,
+                                 void* grad_energy, int ge_dtype,
+                                 int N, int T, int S,
+                                 float eps, int chunk_size, unsigned flags,
+                                 void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Latency loss next to the expected-delay epilogue.
  * DifferentiableAverageLagging as called by MMACriterion.compute_latency_loss
  * (codebase/criterion/mma_criterion.py:172-177) and CIFCriterion.compute_latency_loss

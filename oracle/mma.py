@@ -228,6 +228,43 @@ def mma_process_train(
     return alpha, beta
 
 
+# --------------------------------------------------------------------------- 8f #2 (fixed pre-decision)
+def insert_zeros(x: Tensor, stride: int) -> Tensor:
+    """FixedStrideMonotonicAttention.insert_zeros (modules/fixed_pre_decision.py:85-95): a
+    transposed 1-D convolution with the kernel [0, ..., 0, 1] of width `stride` and that stride,
+    i.e. x[..., k] lands on column (k+1)*stride - 1 of a row of length Sp*stride."""
+    n, t, sp = x.shape
+    weight = torch.nn.functional.pad(torch.ones(1, 1, 1).to(x), (stride - 1, 0))
+    up = torch.nn.functional.conv_transpose1d(x.reshape(-1, sp).unsqueeze(1), weight, stride=stride, padding=0)
+    return up.squeeze(1).view(n, t, -1)
+
+
+def fixed_stride_p_choose(p_choose_pooled: Tensor, src_len: int, ratio: int) -> Tensor:
+    """Tail of FixedStrideMonotonicAttention.p_choose (modules/fixed_pre_decision.py:139-159):
+    zero-upsample, then either append zeros (:141-153, upsampled row shorter than src_len -- the
+    floor-pooled inference case) or cut to src_len and overwrite the last column with the last
+    pooled value (:154-159)."""
+    p = insert_zeros(p_choose_pooled, ratio)
+    n, t, _ = p.shape
+    if p.size(-1) < src_len:
+        p = torch.cat([p, torch.zeros(n, t, src_len - p.size(-1)).to(p)], dim=2)
+    else:
+        p = p[:, :, :src_len]
+        p[:, :, -1] = p_choose_pooled[:, :, -1]
+    return p
+
+
+def mma_process_train_pooled(p_choose_pooled: Tensor, src_len: int, ratio: int,
+                             soft_energy: Optional[Tensor], padding_mask: Optional[Tensor] = None,
+                             eps: float = 1e-6, mass_preserve: bool = True,
+                             chunk_size: Optional[int] = None, compute_dtype: torch.dtype = F32):
+    """monotonic_attention_process_train of a `*_fixed_pre_decision` class after the pooled
+    p_choose_from_qk and the soft-energy bmm.  Returns (p_choose, alpha, beta)."""
+    p = fixed_stride_p_choose(p_choose_pooled, src_len, ratio)
+    alpha, beta = mma_process_train(p, soft_energy, padding_mask, eps, mass_preserve, chunk_size, compute_dtype)
+    return p, alpha, beta
+
+
 # --------------------------------------------------------------------------- a9
 def mma_process_infer(
     p_choose: Tensor,            # [N, S]  (N = bsz * heads), sigmoid(energy), eval mode

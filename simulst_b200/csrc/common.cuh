@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <type_traits>
 
 #include "../../include/simulst_b200.h"
 
@@ -291,6 +292,21 @@ __device__ __forceinline__ void flag_status(unsigned* status, unsigned bits) {
 }
 // prob_check (functions.py:9-17): NaN, or outside [0 - 1e-10, 1 + 1e-10] evaluated in fp32
 // (1 + 1e-10 rounds to 1.0f).
+// One element loaded as raw bits (the consumer converts later, so the load's latency is not
+// waited for at the point of the load) and its conversion.  Zero bits are 0.0 in every type.
+template <typename T>
+__device__ __forceinline__ unsigned ldg_raw(const T* p) {
+    unsigned v;
+    if constexpr (sizeof(T) == 4) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    else asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));      // zero-extended into the 32-bit register
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ float raw_to_f32(unsigned v) {
+    if constexpr (sizeof(T) == 4) return __uint_as_float(v);
+    else if constexpr (std::is_same<T, __nv_bfloat16>::value) return __uint_as_float(v << 16);
+    else return __half2float(__ushort_as_half((unsigned short)v));
+}
 __device__ __forceinline__ unsigned prob_bits(float v) {
     unsigned b = 0u;
     if (v != v) b |= SIMULST_ST_NAN;

@@ -1,4 +1,5 @@
 // C-ABI entry points of the MMA training path (see include/simulst_b200.h).
+#include <algorithm>
 #include <atomic>
 
 #include "mma_common.cuh"
@@ -70,6 +71,69 @@ static int mode_of(unsigned flags, int chunk) {
     return chunk > 0 ? kModeSoftCk : kModeSoftIL;
 }
 
+// ---- pooled p_choose (fixed pre-decision): stand-alone expansion / gradient gather, used when a
+// shape does not qualify for the kernels that expand the row in registers.
+// dense[n,t,j] = pooled[n,t,(j+1)/r - 1] if (j+1) % r == 0, pooled[n,t,Sp-1] if j == S-1, else 0
+// (insert_zeros + slice + last-column assignment, modules/fixed_pre_decision.py:85-95,139-159)
+template <typename T>
+__global__ void pool_expand_kernel(const T* __restrict__ pooled, T* __restrict__ dense, size_t rows, int S, int Sp, int r) {
+    const size_t total = rows * (size_t)S;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = q / S;
+        const int j = (int)(q - row * S);
+        T v = from_f32<T>(0.f);
+        if (j == S - 1) v = pooled[row * Sp + Sp - 1];
+        else if ((j + 1) % r == 0) v = pooled[row * Sp + (j + 1) / r - 1];
+        dense[q] = v;
+    }
+}
+// pooled_grad[n,t,k] = dense_grad[n,t, k == Sp-1 ? S-1 : (k+1)*r - 1]
+template <typename T>
+__global__ void pool_gather_kernel(const T* __restrict__ dense, T* __restrict__ pooled, size_t rows, int S, int Sp, int r) {
+    const size_t total = rows * (size_t)Sp;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = q / Sp;
+        const int k = (int)(q - row * Sp);
+        pooled[q] = dense[row * S + (k == Sp - 1 ? S - 1 : (k + 1) * r - 1)];
+    }
+}
+template <typename T>
+static int run_pool_expand(const void* pooled, void* dense, size_t rows, int S, int Sp, int r, cudaStream_t st) {
+    const size_t total = rows * (size_t)S;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    pool_expand_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(pooled), static_cast<T*>(dense), rows, S, Sp, r);
+    return check_launch();
+}
+template <typename T>
+static int run_pool_gather(const void* dense, void* pooled, size_t rows, int S, int Sp, int r, cudaStream_t st) {
+    const size_t total = rows * (size_t)Sp;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    pool_gather_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(dense), static_cast<T*>(pooled), rows, S, Sp, r);
+    return check_launch();
+}
+
+// Does a pooled call run on the register-expansion kernels?  Mirrors the tests of
+// launch_mma_fwd_pipe_pooled / launch_mma_bwd_fast_pooled for 16-byte aligned tensors.
+static bool pooled_fused_shape(int p_dtype, int S, int ratio, int chunk_size, unsigned flags, bool has_mask,
+                               const Config& cfg, int use_pipe) {
+    if ((use_pipe & 5) != 5 || !g_use_tma.load(std::memory_order_relaxed)) return false;
+    if ((flags & SIMULST_MMA_SOFT) && chunk_size > 0) return false;
+    if (flags & SIMULST_MMA_LEFT_PADDING) return false;
+    if (has_mask && !(flags & SIMULST_MMA_RIGHT_PADDING)) return false;
+    if (cfg.threads > 512 || cfg.vpt > 8 || ratio < cfg.vpt || S % cfg.vpt != 0 || S % 4 != 0) return false;
+    return ((size_t)S * dtype_size(p_dtype)) % 16 == 0;
+}
+
+int mma_fwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int e_dtype,
+                 const uint8_t* padding_mask, float* alpha, float* beta, float* side, float* expected_delays,
+                 int N, int T, int S, float eps, int chunk_size, unsigned flags, unsigned* status, void* stream,
+                 int pool_ratio, void* p_dense);
+int mma_bwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int e_dtype,
+                 const uint8_t* padding_mask, const float* alpha, const float* side, const float* grad_alpha,
+                 const float* grad_beta, const float* grad_expected_delays, void* grad_p, int gp_dtype,
+                 void* grad_energy, int ge_dtype, int N, int T, int S, float eps, int chunk_size, unsigned flags,
+                 void* stream, int pool_ratio, const void* p_dense, void* grad_p_dense);
+
 }  // namespace simulst
 
 using namespace simulst;
@@ -112,6 +176,19 @@ int simulst_mma_train_fwd_delays(const void* p_choose, int p_dtype, const void* 
                                  float* expected_delays,
                                  int N, int T, int S, float eps, int chunk_size, unsigned flags,
                                  unsigned* status, void* stream) {
+    return mma_fwd_core(p_choose, p_dtype, soft_energy, e_dtype, padding_mask, alpha, beta, side, expected_delays,
+                        N, T, S, eps, chunk_size, flags, status, stream, 0, nullptr);
+}
+
+}  // extern "C"
+
+namespace simulst {
+// pool_ratio > 0: p_choose is the pooled [N,T,ceil(S/ratio)] tensor, p_dense the optional dense output
+int mma_fwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int e_dtype,
+                 const uint8_t* padding_mask, float* alpha, float* beta, float* side,
+                 float* expected_delays,
+                 int N, int T, int S, float eps, int chunk_size, unsigned flags,
+                 unsigned* status, void* stream, int pool_ratio, void* p_dense) {
     const bool soft = (flags & SIMULST_MMA_SOFT) != 0u;
     if (p_choose == nullptr || alpha == nullptr || !valid_dtype(p_dtype)) return SIMULST_E_ARG;
     if (soft && (soft_energy == nullptr || beta == nullptr || e_dtype != p_dtype)) return SIMULST_E_ARG;
@@ -132,8 +209,8 @@ int simulst_mma_train_fwd_delays(const void* p_choose, int p_dtype, const void* 
     prm.N = N; prm.T = T; prm.S = S; prm.eps = eps; prm.chunk = chunk_size; prm.flags = flags;
     prm.status = status;
     const int use_pipe = g_use_pipe.load(std::memory_order_relaxed);
-    prm.tma = g_use_tma.load(std::memory_order_relaxed) && ((size_t)S * esz) % 16 == 0 && aligned(p_choose, 16) &&
-              (!soft || aligned(soft_energy, 16));
+    prm.tma = g_use_tma.load(std::memory_order_relaxed) && ((size_t)S * esz) % 16 == 0 &&
+              (pool_ratio > 0 || aligned(p_choose, 16)) && (!soft || aligned(soft_energy, 16));
     prm.vec_out = (S % 4 == 0) && aligned(alpha, 16) && (!soft || aligned(beta, 16));
     prm.pipe = use_pipe & 1;
 
@@ -147,6 +224,26 @@ int simulst_mma_train_fwd_delays(const void* p_choose, int p_dtype, const void* 
             default: return mma_fwd_dispatch_f16(q, mode, cfg.threads, cfg.vpt, st);
         }
     };
+    if (pool_ratio > 0) {
+        const int Sp = (S + pool_ratio - 1) / pool_ratio;
+        if (p_dense != nullptr && !aligned(p_dense, 16)) return SIMULST_E_ALIGN;
+        if (pooled_fused_shape(p_dtype, S, pool_ratio, chunk_size, flags, padding_mask != nullptr, cfg, use_pipe) &&
+            prm.tma && prm.vec_out) {
+            MmaParams q = prm;
+            q.pool_ratio = pool_ratio; q.Sp = Sp; q.p_dense = p_dense;
+            const int prc = run(q);
+            if (prc != 1) return prc;
+        }
+        // the shape does not qualify: expand the row once, then the dense path
+        if (p_dense == nullptr) return SIMULST_E_ARG;
+        const size_t rows = (size_t)N * T;
+        const int xrc = p_dtype == SIMULST_F32 ? run_pool_expand<float>(p_choose, p_dense, rows, S, Sp, pool_ratio, st)
+                      : p_dtype == SIMULST_BF16 ? run_pool_expand<__nv_bfloat16>(p_choose, p_dense, rows, S, Sp, pool_ratio, st)
+                                                : run_pool_expand<__half>(p_choose, p_dense, rows, S, Sp, pool_ratio, st);
+        if (xrc != SIMULST_OK) return xrc;
+        prm.p = p_dense;
+        prm.tma = prm.tma && aligned(p_dense, 16);
+    }
     if (split_masked_call(prm, mode, cfg, prm.pipe != 0)) {
         // pass 1: rows whose mask is a right-padding mask, through the dense kernels;
         // pass 2: every other row, element-by-element mask handling.  Each CTA decides from its
@@ -162,6 +259,10 @@ int simulst_mma_train_fwd_delays(const void* p_choose, int p_dtype, const void* 
     }
     return run(prm);
 }
+
+}  // namespace simulst
+
+extern "C" {
 
 int simulst_mma_train_bwd(const void* p_choose, int p_dtype, const void* soft_energy, int e_dtype,
                           const uint8_t* padding_mask, const float* alpha, const float* side,
@@ -181,6 +282,24 @@ int simulst_mma_train_bwd_delays(const void* p_choose, int p_dtype, const void* 
                                  void* grad_p, int gp_dtype, void* grad_energy, int ge_dtype,
                                  int N, int T, int S, float eps, int chunk_size, unsigned flags,
                                  void* stream) {
+    return mma_bwd_core(p_choose, p_dtype, soft_energy, e_dtype, padding_mask, alpha, side, grad_alpha, grad_beta,
+                        grad_expected_delays, grad_p, gp_dtype, grad_energy, ge_dtype, N, T, S, eps, chunk_size,
+                        flags, stream, 0, nullptr, nullptr);
+}
+
+}  // extern "C"
+
+namespace simulst {
+// pool_ratio > 0: p_choose / grad_p are the pooled [N,T,ceil(S/ratio)] tensors; p_dense (the
+// forward's dense expansion) and grad_p_dense (workspace) serve shapes that do not qualify for
+// the register-expansion kernel
+int mma_bwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int e_dtype,
+                 const uint8_t* padding_mask, const float* alpha, const float* side,
+                 const float* grad_alpha, const float* grad_beta,
+                 const float* grad_expected_delays,
+                 void* grad_p, int gp_dtype, void* grad_energy, int ge_dtype,
+                 int N, int T, int S, float eps, int chunk_size, unsigned flags,
+                 void* stream, int pool_ratio, const void* p_dense, void* grad_p_dense) {
     const bool soft = (flags & SIMULST_MMA_SOFT) != 0u;
     const bool mp = (flags & SIMULST_MMA_MASS_PRESERVATION) != 0u;
     if (p_choose == nullptr || alpha == nullptr || grad_p == nullptr || !valid_dtype(p_dtype)) return SIMULST_E_ARG;
@@ -205,9 +324,10 @@ int simulst_mma_train_bwd_delays(const void* p_choose, int p_dtype, const void* 
     prm.g_p = grad_p; prm.g_e = soft ? grad_energy : nullptr;
     prm.N = N; prm.T = T; prm.S = S; prm.eps = eps; prm.chunk = chunk_size; prm.flags = flags;
     prm.status = nullptr;
-    const bool a16 = aligned(p_choose, 16) && (!soft || aligned(soft_energy, 16)) && aligned(alpha, 16) &&
+    const bool a16 = (pool_ratio > 0 || (aligned(p_choose, 16) && aligned(grad_p, 16))) &&
+                     (!soft || aligned(soft_energy, 16)) && aligned(alpha, 16) &&
                      (grad_alpha == nullptr || aligned(grad_alpha, 16)) &&
-                     (grad_beta == nullptr || aligned(grad_beta, 16)) && aligned(grad_p, 16) &&
+                     (grad_beta == nullptr || aligned(grad_beta, 16)) &&
                      (!soft || aligned(grad_energy, 16));
     const int use_pipe = g_use_pipe.load(std::memory_order_relaxed);
     prm.tma = g_use_tma.load(std::memory_order_relaxed) && ((size_t)S * esz) % 16 == 0 && a16;
@@ -225,6 +345,32 @@ int simulst_mma_train_bwd_delays(const void* p_choose, int p_dtype, const void* 
             default: return mma_bwd_dispatch_f16(q, mode, cfg.threads, cfg.vpt, st);
         }
     };
+    bool gather = false;
+    int Sp = 0;
+    if (pool_ratio > 0) {
+        Sp = (S + pool_ratio - 1) / pool_ratio;
+        if (pooled_fused_shape(p_dtype, S, pool_ratio, chunk_size, flags, padding_mask != nullptr, cfg, use_pipe) &&
+            prm.tma && prm.vec_out) {
+            MmaParams q = prm;
+            q.pool_ratio = pool_ratio; q.Sp = Sp;
+            const int prc = run(q);
+            if (prc != 1) return prc;
+        }
+        if (p_dense == nullptr || grad_p_dense == nullptr) return SIMULST_E_ARG;
+        if (!aligned(p_dense, esz) || !aligned(grad_p_dense, esz)) return SIMULST_E_ALIGN;
+        prm.p = p_dense; prm.g_p = grad_p_dense;
+        const bool d16 = aligned(p_dense, 16) && aligned(grad_p_dense, 16);
+        prm.tma = prm.tma && d16;
+        prm.vec_out = prm.vec_out && d16;
+        gather = true;
+    }
+    auto finish = [&](int code) {
+        if (code != SIMULST_OK || !gather) return code;
+        const size_t rows = (size_t)N * T;
+        return p_dtype == SIMULST_F32 ? run_pool_gather<float>(grad_p_dense, grad_p, rows, S, Sp, pool_ratio, st)
+             : p_dtype == SIMULST_BF16 ? run_pool_gather<__nv_bfloat16>(grad_p_dense, grad_p, rows, S, Sp, pool_ratio, st)
+                                       : run_pool_gather<__half>(grad_p_dense, grad_p, rows, S, Sp, pool_ratio, st);
+    };
     if (split_masked_call(prm, mode, cfg, prm.fast != 0)) {
         MmaParams a = prm;          // see simulst_mma_train_fwd_delays
         a.flags |= SIMULST_MMA_RIGHT_PADDING;
@@ -233,9 +379,39 @@ int simulst_mma_train_bwd_delays(const void* p_choose, int p_dtype, const void* 
         if (rc != SIMULST_OK) return rc;
         MmaParams b = prm;
         b.row_filter = 2;
-        return run(b);
+        return finish(run(b));
     }
-    return run(prm);
+    return finish(run(prm));
+}
+}  // namespace simulst
+
+extern "C" {
+
+int simulst_mma_pooled_is_fused(int p_dtype, int S, int ratio, int chunk_size, unsigned flags, int has_mask) {
+    if (!valid_dtype(p_dtype) || S <= 0 || S > SIMULST_MMA_MAX_SRC || ratio < 2) return 0;
+    return pooled_fused_shape(p_dtype, S, ratio, chunk_size, flags, has_mask != 0, pick_config(S),
+                              g_use_pipe.load(std::memory_order_relaxed)) ? 1 : 0;
+}
+
+int simulst_mma_train_fwd_pooled(const void* p_pooled, int p_dtype, int ratio, const void* soft_energy, int e_dtype,
+                                 const uint8_t* padding_mask, void* p_dense, float* alpha, float* beta, float* side,
+                                 float* expected_delays, int N, int T, int S, float eps, int chunk_size,
+                                 unsigned flags, unsigned* status, void* stream) {
+    if (ratio < 2) return SIMULST_E_ARG;
+    return mma_fwd_core(p_pooled, p_dtype, soft_energy, e_dtype, padding_mask, alpha, beta, side, expected_delays,
+                        N, T, S, eps, chunk_size, flags, status, stream, ratio, p_dense);
+}
+
+int simulst_mma_train_bwd_pooled(const void* p_pooled, int p_dtype, int ratio, const void* soft_energy, int e_dtype,
+                                 const uint8_t* padding_mask, const void* p_dense, const float* alpha,
+                                 const float* side, const float* grad_alpha, const float* grad_beta,
+                                 const float* grad_expected_delays, void* grad_p_pooled, int gp_dtype,
+                                 void* grad_p_dense, void* grad_energy, int ge_dtype, int N, int T, int S,
+                                 float eps, int chunk_size, unsigned flags, void* stream) {
+    if (ratio < 2) return SIMULST_E_ARG;
+    return mma_bwd_core(p_pooled, p_dtype, soft_energy, e_dtype, padding_mask, alpha, side, grad_alpha, grad_beta,
+                        grad_expected_delays, grad_p_pooled, gp_dtype, grad_energy, ge_dtype, N, T, S, eps,
+                        chunk_size, flags, stream, ratio, p_dense, grad_p_dense);
 }
 
 }  // extern "C"

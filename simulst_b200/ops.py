@@ -143,6 +143,124 @@ def mma_train_with_delays(p_choose: Tensor, soft_energy: Optional[Tensor] = None
     return alpha, beta, delays
 
 
+# ----------------------------------------------------------------------------- pooled p_choose (fixed pre-decision)
+class MMATrainPooledFunction(torch.autograd.Function):
+    """(p_choose_pooled [N,T,ceil(S/ratio)], soft_energy [N,T,S]) -> (alpha, beta, delays, p_choose):
+    FixedStrideMonotonicAttention.insert_zeros + the tail of its p_choose()
+    (reference codebase/modules/fixed_pre_decision.py:85-95, :139-159) fused with steps 2-3 of
+    monotonic_attention_process_train.  The zero-upsampled row is formed in registers; the dense
+    p_choose is written only when ``want_dense`` (the reference returns it in the attention dict,
+    nothing differentiates through it: it comes back non-differentiable)."""
+
+    @staticmethod
+    def forward(ctx, p_pooled: Tensor, soft_energy: Optional[Tensor], padding_mask: Optional[Tensor],
+                src_len: int, ratio: int, eps: float, mass_preservation: bool, chunk_size: Optional[int],
+                with_delays: bool, want_dense: bool, right_padding: bool):
+        lib = _lib.load()
+        dev = _lib.require_cuda(p_pooled, soft_energy, padding_mask)
+        if p_pooled.dim() != 3:
+            raise ValueError("p_choose_pooled must be [bsz*heads, tgt_len, ceil(src_len / ratio)]")
+        n, t, sp = p_pooled.shape
+        s, ratio = int(src_len), int(ratio)
+        if ratio < 2 or sp != (s + ratio - 1) // ratio:
+            raise ValueError(f"p_choose_pooled has {sp} columns, expected ceil({s} / {ratio})")
+        if s > _lib.MMA_MAX_SRC:
+            raise ValueError(f"src_len {s} exceeds the on-chip row limit {_lib.MMA_MAX_SRC}")
+        soft = soft_energy is not None
+        p = p_pooled.contiguous()
+        e = None
+        flags = 0
+        if soft:
+            if tuple(soft_energy.shape) != (n, t, s):
+                raise ValueError("soft_energy must be [bsz*heads, tgt_len, src_len]")
+            if soft_energy.dtype == torch.float16:
+                flags |= _lib.MMA_ENERGY_F16_FILL
+            e = soft_energy.contiguous()
+            if e.dtype != p.dtype:
+                common = torch.promote_types(e.dtype, p.dtype)
+                e, p = e.to(common), p.to(common)
+            flags |= _lib.MMA_SOFT
+        if mass_preservation:
+            flags |= _lib.MMA_MASS_PRESERVATION
+        mask = _mask_u8(padding_mask, n, s, dev)
+        if mask is not None and (right_padding or _lib.right_padding_assumed()):
+            flags |= _lib.MMA_RIGHT_PADDING
+        chunk = int(chunk_size) if chunk_size else 0
+        fused = bool(lib.simulst_mma_pooled_is_fused(_lib.dtype_enum(p.dtype), s, ratio, chunk, flags,
+                                                     1 if mask is not None else 0))
+        need_dense = want_dense or not fused
+        p_dense = torch.empty((n, t, s), dtype=p.dtype, device=dev) if need_dense else None
+        alpha = torch.empty((n, t, s), dtype=torch.float32, device=dev)
+        beta = torch.empty((n, t, s), dtype=torch.float32, device=dev) if soft else None
+        small = torch.zeros if mask is not None else torch.empty
+        side = small((n, t, 2), dtype=torch.float32, device=dev) if mass_preservation else None
+        delays = small((n, t), dtype=torch.float32, device=dev) if with_delays else None
+        status = _lib.status_word(dev)
+        with torch.cuda.device(dev):
+            rc = lib.simulst_mma_train_fwd_pooled(
+                _lib.ptr(p), _lib.dtype_enum(p.dtype), ratio, _lib.ptr(e),
+                _lib.dtype_enum(e.dtype) if soft else 0, _lib.ptr(mask), _lib.ptr(p_dense),
+                _lib.ptr(alpha), _lib.ptr(beta), _lib.ptr(side), _lib.ptr(delays),
+                n, t, s, float(eps), chunk, flags, _lib.ptr(status), _lib.stream_ptr(dev))
+        _lib.check(rc, "simulst_mma_train_fwd_pooled")
+        _lib.maybe_check(dev)
+        ctx.save_for_backward(p, e, mask, alpha, side, None if fused else p_dense)
+        ctx.cfg = (n, t, s, ratio, float(eps), chunk, flags, soft, fused)
+        ctx.in_dtypes = (p_pooled.dtype, soft_energy.dtype if soft else None)
+        ctx.set_materialize_grads(False)
+        out_dense = p_dense if want_dense else alpha.new_empty(0)
+        if out_dense.dtype != p_pooled.dtype:
+            out_dense = out_dense.to(p_pooled.dtype)
+        ctx.mark_non_differentiable(out_dense)
+        return (alpha, beta if soft else alpha.new_empty(0),
+                delays if with_delays else alpha.new_empty(0), out_dense)
+
+    @staticmethod
+    def backward(ctx, g_alpha, g_beta, g_delays, _g_dense):
+        lib = _lib.load()
+        p, e, mask, alpha, side, p_dense = ctx.saved_tensors
+        n, t, s, ratio, eps, chunk, flags, soft, fused = ctx.cfg
+        dev = p.device
+        ga = g_alpha.contiguous().float() if g_alpha is not None else None
+        gb = g_beta.contiguous().float() if (soft and g_beta is not None) else None
+        gd = g_delays.contiguous().float() if (g_delays is not None and g_delays.numel() == n * t) else None
+        grad_p = torch.empty_like(p)
+        grad_e = torch.empty_like(e) if soft else None
+        grad_dense = None if fused else torch.empty((n, t, s), dtype=p.dtype, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.simulst_mma_train_bwd_pooled(
+                _lib.ptr(p), _lib.dtype_enum(p.dtype), ratio, _lib.ptr(e),
+                _lib.dtype_enum(e.dtype) if soft else 0, _lib.ptr(mask), _lib.ptr(p_dense),
+                _lib.ptr(alpha), _lib.ptr(side), _lib.ptr(ga), _lib.ptr(gb), _lib.ptr(gd),
+                _lib.ptr(grad_p), _lib.dtype_enum(p.dtype), _lib.ptr(grad_dense), _lib.ptr(grad_e),
+                _lib.dtype_enum(e.dtype) if soft else 0,
+                n, t, s, eps, chunk, flags, _lib.stream_ptr(dev))
+        _lib.check(rc, "simulst_mma_train_bwd_pooled")
+        p_dt, e_dt = ctx.in_dtypes
+        if grad_p.dtype != p_dt:
+            grad_p = grad_p.to(p_dt)
+        if soft and grad_e.dtype != e_dt:
+            grad_e = grad_e.to(e_dt)
+        return (grad_p, grad_e) + (None,) * 9
+
+
+def mma_train_pooled(p_choose_pooled: Tensor, src_len: int, ratio: int,
+                     soft_energy: Optional[Tensor] = None, padding_mask: Optional[Tensor] = None,
+                     eps: float = 1e-6, mass_preservation: bool = True, chunk_size: Optional[int] = None,
+                     with_delays: bool = False, want_dense: bool = True, right_padding: bool = False):
+    """Fixed pre-decision training path from the POOLED p_choose.
+    Returns (p_choose [N,T,S] or None, alpha, beta, expected_delays or None); beta is alpha for hard
+    attention.  ``right_padding=True`` is the caller's promise that ``padding_mask`` is a
+    right-padding mask (verified on the device: a violation poisons the outputs with NaN and sets
+    SIMULST_ST_NOT_RIGHT_PADDED); without it a masked call expands the row and runs the dense path."""
+    alpha, beta, delays, dense = MMATrainPooledFunction.apply(
+        p_choose_pooled, soft_energy, padding_mask, src_len, ratio, eps, mass_preservation, chunk_size,
+        with_delays, want_dense, right_padding)
+    if soft_energy is None:
+        beta = alpha
+    return (dense if want_dense else None), alpha, beta, (delays if with_delays else None)
+
+
 # ----------------------------------------------------------------------------- stand-alone MMA pieces
 class SoftAttentionFunction(torch.autograd.Function):
     """expected_soft_attention as its own operator

@@ -213,8 +213,83 @@ def gen_ssnt():
     return _save("ssnt.npz", out, names)
 
 
+# ----------------------------------------------------------------------------- fixed pre-decision
+FIXED_CASES = [
+    # name, kind, ratio, pool, bsz, heads, T, S, masked, mass_preservation
+    ("il_r8_div",      "infinite_lookback", 8, "average", 2, 2, 6, 64,  False, True),
+    ("il_r8_tail",     "infinite_lookback", 8, "average", 2, 2, 5, 61,  False, True),
+    ("il_r8_mask",     "infinite_lookback", 8, "average", 3, 2, 5, 72,  True,  True),
+    ("il_r8_tailmask", "infinite_lookback", 8, "last",    3, 2, 4, 75,  True,  True),
+    ("hard_r4_tail",   "hard_aligned",      4, "last",    2, 2, 5, 30,  False, True),
+    ("hard_r8_mask",   "hard_aligned",      8, "average", 2, 4, 4, 48,  True,  False),
+    ("il_r8_short",    "infinite_lookback", 8, "average", 2, 2, 3, 5,   False, True),
+    ("il_r3_odd",      "infinite_lookback", 3, "average", 2, 2, 4, 32,  False, True),
+    ("il_r16_long",    "infinite_lookback", 16, "average", 1, 2, 8, 264, True, True),
+]
+
+
+def gen_fixed_predecision():
+    """The real wrapper classes (modules/fixed_pre_decision.py:175-190) run through their own
+    monotonic_attention_process_train; p_choose_from_qk and energy_from_qk are wrapped on the
+    instance only to RECORD the pooled p_choose and the soft energy they return (the two tensors
+    the kernels take), with retain_grad so their autograd gradients are stored too."""
+    out, names = {}, []
+    for idx, (name, kind, ratio, pool, bsz, heads, t, s, masked, mp) in enumerate(FIXED_CASES):
+        embed = 8 * heads
+        att = ref_loader.make_fixed_pre_decision_attention(kind, ratio, pool, embed, heads,
+                                                           mass_preservation=mp, seed=7000 + idx)
+        att.train()
+        att.noise_std = 0.0
+        g = torch.Generator().manual_seed(7100 + idx)
+        q = torch.randn(t, bsz, embed, generator=g)
+        k = torch.randn(s, bsz, embed, generator=g) * 1.5
+        mask = None
+        if masked:
+            lens = torch.randint(max(2, s // 2), s + 1, (bsz,), generator=g)
+            lens[0] = s
+            mask = (torch.arange(s)[None, :] >= lens[:, None]).repeat_interleave(heads, 0)
+        rec = {}
+        orig_p, orig_e = att.p_choose_from_qk, att.energy_from_qk
+
+        def rec_p(*a, **kw):
+            v = orig_p(*a, **kw)
+            v.retain_grad()
+            rec["p_pooled"] = v
+            return v
+
+        def rec_e(query, key, energy_type, **kw):
+            v = orig_e(query, key, energy_type, **kw)
+            if energy_type == "soft":
+                v.retain_grad()
+                rec["soft_energy"] = v
+            return v
+        att.p_choose_from_qk, att.energy_from_qk = rec_p, rec_e
+        p_choose, alpha, beta, _ = att.monotonic_attention_process_train(q, k, mask)
+        soft = kind != "hard_aligned"
+        n = bsz * heads
+        g_alpha = torch.randn(n, t, s, generator=g)
+        g_beta = torch.randn(n, t, s, generator=g)
+        loss = (alpha * g_alpha).sum()
+        if soft:
+            loss = loss + (beta * g_beta).sum()
+        loss.backward()
+        names.append(name)
+        out[f"{name}/cfg"] = np.array([n, t, s, ratio, int(masked), int(soft), int(mp)], np.int64)
+        out[f"{name}/p_pooled"] = _np(rec["p_pooled"])
+        out[f"{name}/grad_p_pooled"] = _np(rec["p_pooled"].grad)
+        out[f"{name}/p_choose"] = _np(p_choose)
+        out[f"{name}/soft_energy"] = _np(rec["soft_energy"]) if soft else np.zeros((0,), np.float32)
+        out[f"{name}/grad_soft_energy"] = _np(rec["soft_energy"].grad) if soft else np.zeros((0,), np.float32)
+        out[f"{name}/mask"] = _np(mask) if mask is not None else np.zeros((0,), bool)
+        out[f"{name}/g_alpha"] = _np(g_alpha)
+        out[f"{name}/g_beta"] = _np(g_beta)
+        out[f"{name}/alpha"] = _np(alpha)
+        out[f"{name}/beta"] = _np(beta)
+    return _save("fixed_predecision.npz", out, names)
+
+
 GENERATORS = [("waitk", gen_waitk), ("latency", gen_latency), ("mma_leftpad", gen_leftpad),
-              ("ssnt", gen_ssnt)]
+              ("ssnt", gen_ssnt), ("fixed_predecision", gen_fixed_predecision)]
 
 
 if __name__ == "__main__":

@@ -8,6 +8,7 @@ from tests.golden_io import load, opt
 
 WAITK = load("waitk.npz")
 LEFT = load("mma_leftpad.npz")
+FIXED = load("fixed_predecision.npz")
 
 
 @pytest.mark.parametrize("name", list(WAITK))
@@ -40,3 +41,24 @@ def test_left_padding_oracle_matches_golden():
     (a * c.g_alpha).sum().backward()
     torch.testing.assert_close(a, c.alpha, rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(p.grad, c.grad_p, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", list(FIXED))
+def test_fixed_pre_decision_oracle_matches_golden(name):
+    """8f #2: insert_zeros + tail fix-up + the training path, restated, against what the reference's
+    own *_fixed_pre_decision classes produced (outputs bit-identical, autograd gradients of the
+    POOLED p_choose and of the soft energy)."""
+    c = FIXED[name]
+    n, t, s, ratio, masked, soft, mp = [int(v) for v in c.cfg]
+    pp = c.p_pooled.clone().requires_grad_()
+    se = c.soft_energy.clone().requires_grad_() if soft else None
+    p, alpha, beta = omma.mma_process_train_pooled(pp, s, ratio, se, opt(c.mask), 1e-6, bool(mp))
+    assert torch.equal(p, c.p_choose)
+    loss = (alpha * c.g_alpha).sum()
+    if soft:
+        loss = loss + (beta * c.g_beta).sum()
+    loss.backward()
+    assert torch.equal(alpha, c.alpha) and torch.equal(beta, c.beta)
+    torch.testing.assert_close(pp.grad, c.grad_p_pooled, rtol=1e-6, atol=1e-7)
+    if soft:
+        torch.testing.assert_close(se.grad, c.grad_soft_energy, rtol=1e-6, atol=1e-7)
