@@ -188,26 +188,39 @@ int simulst_mma_train_bwd_delays(const void* p_choose, int p_dtype,
  *     dense[n,t,j] = pooled[n,t,(j+1)/ratio - 1]   if (j+1) % ratio == 0
  *                  = pooled[n,t,Sp-1]              if j == S-1     (:156-159)
  *                  = 0                             otherwise
- * The kernels form that row in registers (1/ratio of the p_choose bytes are read, none staged)
- * when simulst_mma_pooled_is_fused() says so: hard or infinite-lookback attention, ratio >= the
- * per-thread element count (8; 4 for S <= 128), S <= 4096, S*esize a multiple of 16 bytes, and
- * either no padding mask or the SIMULST_MMA_RIGHT_PADDING promise (forward() asserts right padding,
- * monotonic_multihead_attention.py:378-381; the kernel verifies the promise).  Every other shape
- * is served by expanding into `p_dense` and running the dense kernels, bit-identical results.
+ * alpha is zero off that grid, so the T-sequential recurrence (and its backward) runs on
+ * [N,T,Sp] only; the expected soft attention, whose rows are independent, and the dense alpha /
+ * beta outputs are produced by streaming row kernels (csrc/mma_sparse.cu, four launches per
+ * forward + backward).  That path serves: hard or infinite-lookback attention, S <= 4096 with
+ * S*esize a multiple of 16 bytes, 16-byte aligned tensors, and either no padding mask or the
+ * SIMULST_MMA_RIGHT_PADDING promise (forward() asserts right padding,
+ * monotonic_multihead_attention.py:378-381; the kernels verify the promise per row) --
+ * simulst_mma_pooled_is_fused() answers for a shape.  Every other shape is served by expanding
+ * into `p_dense` and running the dense kernels.
  *
  *   p_pooled       [N,T,Sp] p_dtype
  *   p_dense        [N,T,S]  p_dtype out   the zero-upsampled p_choose the reference's
  *                                         process_train returns; optional (NULL) when the call is
  *                                         fused, required otherwise (it is then also the workspace)
+ *   workspace      simulst_mma_pooled_workspace_bytes(N,T,S,ratio) bytes, 256-byte aligned,
+ *                  written by the forward call and read by the backward call of the same step
+ *                  (alpha on the grid and per-row geometry; scratch for the gradient on the grid).
+ *                  NULL: the call takes the expand + dense path.
  *   grad_p_pooled  [N,T,Sp] gp_dtype out  gradient w.r.t. p_pooled (each pooled element owns one
- *                                         dense column, so this is a gather of the dense gradient)
+ *                                         dense column)
  *   grad_p_dense   [N,T,S]  workspace     required (with p_dense) when the call is not fused
- * All other arguments as in simulst_mma_train_{fwd,bwd}_delays. */
+ * All other arguments as in simulst_mma_train_{fwd,bwd}_delays (`alpha` of the backward call is
+ * not read on the fused path). */
 int simulst_mma_pooled_is_fused(int p_dtype, int S, int ratio, int chunk_size, unsigned flags, int has_mask);
+long long simulst_mma_pooled_workspace_bytes(int N, int T, int S, int ratio);
+/* 1 (default): pooled calls use the pooled-grid kernels when the shape qualifies; 0: always expand
+ * + dense kernels (development knob, same results within the parity tolerance) */
+int simulst_mma_set_pooled_grid(int enable);
 int simulst_mma_train_fwd_pooled(const void* p_pooled, int p_dtype, int ratio,
                                  const void* soft_energy, int e_dtype,
                                  const uint8_t* padding_mask, void* p_dense,
                                  float* alpha, float* beta, float* side, float* expected_delays,
+                                 void* workspace,
                                  int N, int T, int S,
                                  float eps, int chunk_size, unsigned flags,
                                  unsigned* status, void* stream);
@@ -219,6 +232,7 @@ int simulst_mma_train_bwd_pooled(const void* p_pooled, int p_dtype, int ratio,
                                  const float* grad_expected_delays,
                                  void* grad_p_pooled, int gp_dtype, void* grad_p_dense,
                                  void* grad_energy, int ge_dtype,
+                                 void* workspace,
                                  int N, int T, int S,
                                  float eps, int chunk_size, unsigned flags,
                                  void* stream);

@@ -59,13 +59,15 @@ SIGNATURES = {
                                              c_void_p, c_int, c_void_p, c_int,
                                              c_int, c_int, c_int, c_float, c_int, c_uint, c_void_p]),
     "simulst_mma_pooled_is_fused": (c_int, [c_int, c_int, c_int, c_int, c_uint, c_int]),
+    "simulst_mma_pooled_workspace_bytes": (c_longlong, [c_int, c_int, c_int, c_int]),
+    "simulst_mma_set_pooled_grid": (c_int, [c_int]),
     "simulst_mma_train_fwd_pooled": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
-                                             c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_int, c_int, c_int, c_float, c_int, c_uint,
                                              c_void_p, c_void_p]),
     "simulst_mma_train_bwd_pooled": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                             c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                             c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                              c_int, c_int, c_int, c_float, c_int, c_uint, c_void_p]),
     "simulst_dal_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "simulst_dal_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,

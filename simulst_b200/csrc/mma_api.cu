@@ -4,6 +4,7 @@
 
 #include "mma_common.cuh"
 #include "mma_dispatch.h"
+#include "mma_sparse.h"
 
 namespace simulst {
 
@@ -54,6 +55,7 @@ static int check_device() {
     return c == 1 ? SIMULST_OK : SIMULST_E_ARCH;
 }
 
+static std::atomic<int> g_pooled_grid{1};      // pooled calls: pooled-grid kernels (1) or always expand + dense kernels (0)
 static std::atomic<int> g_split_masked{1};     // masked calls: dense pass for right-padded rows + general pass for the rest
 
 // A masked call is split when the dense kernels can take the right-padded rows: hard or
@@ -112,27 +114,48 @@ static int run_pool_gather(const void* dense, void* pooled, size_t rows, int S, 
     return check_launch();
 }
 
-// Does a pooled call run on the register-expansion kernels?  Mirrors the tests of
-// launch_mma_fwd_pipe_pooled / launch_mma_bwd_fast_pooled for 16-byte aligned tensors.
-static bool pooled_fused_shape(int p_dtype, int S, int ratio, int chunk_size, unsigned flags, bool has_mask,
-                               const Config& cfg, int use_pipe) {
-    if ((use_pipe & 5) != 5 || !g_use_tma.load(std::memory_order_relaxed)) return false;
+// Does a pooled call run on the pooled-grid kernels (mma_sparse.cu)?  Hard or infinite-lookback
+// attention, no left-padding semantics, a padding mask only with the right-padding promise,
+// TMA-legal rows (S * esize a multiple of 16 bytes) of at most 4096 frames.
+static bool pooled_fused_shape(int p_dtype, int S, int ratio, int chunk_size, unsigned flags, bool has_mask) {
+    if (!g_use_tma.load(std::memory_order_relaxed) || !g_pooled_grid.load(std::memory_order_relaxed)) return false;
     if ((flags & SIMULST_MMA_SOFT) && chunk_size > 0) return false;
     if (flags & SIMULST_MMA_LEFT_PADDING) return false;
     if (has_mask && !(flags & SIMULST_MMA_RIGHT_PADDING)) return false;
-    if (cfg.threads > 512 || cfg.vpt > 8 || ratio < cfg.vpt || S % cfg.vpt != 0 || S % 4 != 0) return false;
+    if (ratio < 2 || S > 4096) return false;
     return ((size_t)S * dtype_size(p_dtype)) % 16 == 0;
 }
+
+// Workspace of the pooled-grid path, carried from the forward to the backward call:
+// [a_sp N*T*Sp f32][g_sp N*T*Sp f32][a_x N*T f32][g_x4 N*T float4][mp_info N*T float4][lens N i32][xcol N i32],
+// segments padded to 256 bytes.
+struct PooledWs {
+    size_t off_asp, off_gsp, off_ax, off_gx, off_info, off_lens, off_xcol, total;
+    PooledWs(int N, int T, int Sp) {
+        auto pad = [](size_t b) { return (b + 255) / 256 * 256; };
+        const size_t grid = pad((size_t)N * T * Sp * 4), row = pad((size_t)N * T * 4), row4 = pad((size_t)N * T * 16),
+                     per_n = pad((size_t)N * 4);
+        off_asp = 0; off_gsp = grid; off_ax = 2 * grid; off_gx = off_ax + row; off_info = off_gx + row4;
+        off_lens = off_info + row4; off_xcol = off_lens + per_n; total = off_xcol + per_n;
+    }
+    void bind(SparseParams& q, void* ws) const {
+        unsigned char* b = static_cast<unsigned char*>(ws);
+        q.a_sp = reinterpret_cast<float*>(b + off_asp); q.g_sp = reinterpret_cast<float*>(b + off_gsp);
+        q.a_x = reinterpret_cast<float*>(b + off_ax); q.g_x4 = reinterpret_cast<float4*>(b + off_gx);
+        q.mp_info = reinterpret_cast<float4*>(b + off_info);
+        q.lens = reinterpret_cast<int*>(b + off_lens); q.xcol = reinterpret_cast<int*>(b + off_xcol);
+    }
+};
 
 int mma_fwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int e_dtype,
                  const uint8_t* padding_mask, float* alpha, float* beta, float* side, float* expected_delays,
                  int N, int T, int S, float eps, int chunk_size, unsigned flags, unsigned* status, void* stream,
-                 int pool_ratio, void* p_dense);
+                 int pool_ratio, void* p_dense, void* workspace);
 int mma_bwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int e_dtype,
                  const uint8_t* padding_mask, const float* alpha, const float* side, const float* grad_alpha,
                  const float* grad_beta, const float* grad_expected_delays, void* grad_p, int gp_dtype,
                  void* grad_energy, int ge_dtype, int N, int T, int S, float eps, int chunk_size, unsigned flags,
-                 void* stream, int pool_ratio, const void* p_dense, void* grad_p_dense);
+                 void* stream, int pool_ratio, const void* p_dense, void* grad_p_dense, void* workspace);
 
 }  // namespace simulst
 
@@ -177,7 +200,7 @@ int simulst_mma_train_fwd_delays(const void* p_choose, int p_dtype, const void* 
                                  int N, int T, int S, float eps, int chunk_size, unsigned flags,
                                  unsigned* status, void* stream) {
     return mma_fwd_core(p_choose, p_dtype, soft_energy, e_dtype, padding_mask, alpha, beta, side, expected_delays,
-                        N, T, S, eps, chunk_size, flags, status, stream, 0, nullptr);
+                        N, T, S, eps, chunk_size, flags, status, stream, 0, nullptr, nullptr);
 }
 
 }  // extern "C"
@@ -188,9 +211,12 @@ int mma_fwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
                  const uint8_t* padding_mask, float* alpha, float* beta, float* side,
                  float* expected_delays,
                  int N, int T, int S, float eps, int chunk_size, unsigned flags,
-                 unsigned* status, void* stream, int pool_ratio, void* p_dense) {
+                 unsigned* status, void* stream, int pool_ratio, void* p_dense, void* workspace) {
     const bool soft = (flags & SIMULST_MMA_SOFT) != 0u;
-    if (p_choose == nullptr || alpha == nullptr || !valid_dtype(p_dtype)) return SIMULST_E_ARG;
+    // the dense alpha output is optional on the pooled-grid path (soft attention only: the caller
+    // then consumes alpha through beta and the expected delays)
+    const bool alpha_optional = pool_ratio > 0 && soft && workspace != nullptr && p_dense == nullptr;
+    if (p_choose == nullptr || (alpha == nullptr && !alpha_optional) || !valid_dtype(p_dtype)) return SIMULST_E_ARG;
     if (soft && (soft_energy == nullptr || beta == nullptr || e_dtype != p_dtype)) return SIMULST_E_ARG;
     if (chunk_size < 0) return SIMULST_E_ARG;
     if (N < 0 || T < 0 || S < 0 || S > SIMULST_MMA_MAX_SRC) return SIMULST_E_SHAPE;
@@ -227,12 +253,18 @@ int mma_fwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
     if (pool_ratio > 0) {
         const int Sp = (S + pool_ratio - 1) / pool_ratio;
         if (p_dense != nullptr && !aligned(p_dense, 16)) return SIMULST_E_ALIGN;
-        if (pooled_fused_shape(p_dtype, S, pool_ratio, chunk_size, flags, padding_mask != nullptr, cfg, use_pipe) &&
-            prm.tma && prm.vec_out) {
-            MmaParams q = prm;
-            q.pool_ratio = pool_ratio; q.Sp = Sp; q.p_dense = p_dense;
-            const int prc = run(q);
-            if (prc != 1) return prc;
+        const bool a16 = (!soft || (aligned(soft_energy, 16) && aligned(beta, 16))) && aligned(alpha, 16);
+        if (alpha == nullptr && !(workspace != nullptr && aligned(workspace, 256) && a16 &&
+                                  pooled_fused_shape(p_dtype, S, pool_ratio, chunk_size, flags, padding_mask != nullptr)))
+            return SIMULST_E_ARG;           // only the pooled-grid kernels can skip the dense alpha
+        if (workspace != nullptr && aligned(workspace, 256) && a16 &&
+            pooled_fused_shape(p_dtype, S, pool_ratio, chunk_size, flags, padding_mask != nullptr)) {
+            SparseParams q{};
+            q.pp = p_choose; q.e = prm.e; q.mask = padding_mask; q.alpha = alpha; q.beta = prm.beta;
+            q.p_dense = p_dense; q.side = side; q.delays = expected_delays;
+            q.N = N; q.T = T; q.S = S; q.Sp = Sp; q.r = pool_ratio; q.eps = eps; q.flags = flags; q.status = status;
+            PooledWs(N, T, Sp).bind(q, workspace);
+            return mma_sparse_run(q, p_dtype, false, st);
         }
         // the shape does not qualify: expand the row once, then the dense path
         if (p_dense == nullptr) return SIMULST_E_ARG;
@@ -284,7 +316,7 @@ int simulst_mma_train_bwd_delays(const void* p_choose, int p_dtype, const void* 
                                  void* stream) {
     return mma_bwd_core(p_choose, p_dtype, soft_energy, e_dtype, padding_mask, alpha, side, grad_alpha, grad_beta,
                         grad_expected_delays, grad_p, gp_dtype, grad_energy, ge_dtype, N, T, S, eps, chunk_size,
-                        flags, stream, 0, nullptr, nullptr);
+                        flags, stream, 0, nullptr, nullptr, nullptr);
 }
 
 }  // extern "C"
@@ -299,10 +331,12 @@ int mma_bwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
                  const float* grad_expected_delays,
                  void* grad_p, int gp_dtype, void* grad_energy, int ge_dtype,
                  int N, int T, int S, float eps, int chunk_size, unsigned flags,
-                 void* stream, int pool_ratio, const void* p_dense, void* grad_p_dense) {
+                 void* stream, int pool_ratio, const void* p_dense, void* grad_p_dense, void* workspace) {
     const bool soft = (flags & SIMULST_MMA_SOFT) != 0u;
     const bool mp = (flags & SIMULST_MMA_MASS_PRESERVATION) != 0u;
-    if (p_choose == nullptr || alpha == nullptr || grad_p == nullptr || !valid_dtype(p_dtype)) return SIMULST_E_ARG;
+    if (p_choose == nullptr || (alpha == nullptr && !(pool_ratio > 0 && workspace != nullptr)) || grad_p == nullptr ||
+        !valid_dtype(p_dtype))
+        return SIMULST_E_ARG;
     if (gp_dtype != p_dtype) return SIMULST_E_ARG;
     if (soft && (soft_energy == nullptr || grad_energy == nullptr || e_dtype != p_dtype || ge_dtype != p_dtype))
         return SIMULST_E_ARG;
@@ -349,12 +383,18 @@ int mma_bwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
     int Sp = 0;
     if (pool_ratio > 0) {
         Sp = (S + pool_ratio - 1) / pool_ratio;
-        if (pooled_fused_shape(p_dtype, S, pool_ratio, chunk_size, flags, padding_mask != nullptr, cfg, use_pipe) &&
-            prm.tma && prm.vec_out) {
-            MmaParams q = prm;
-            q.pool_ratio = pool_ratio; q.Sp = Sp;
-            const int prc = run(q);
-            if (prc != 1) return prc;
+        const bool s16 = (!soft || (aligned(soft_energy, 16) && aligned(grad_energy, 16))) &&
+                         (grad_alpha == nullptr || aligned(grad_alpha, 16)) &&
+                         (grad_beta == nullptr || aligned(grad_beta, 16));
+        if (workspace != nullptr && aligned(workspace, 256) && s16 &&
+            pooled_fused_shape(p_dtype, S, pool_ratio, chunk_size, flags, padding_mask != nullptr)) {
+            SparseParams q{};
+            q.pp = p_choose; q.e = prm.e; q.mask = padding_mask; q.side = prm.side;
+            q.g_alpha = grad_alpha; q.g_beta = prm.g_beta; q.g_delays = grad_expected_delays;
+            q.g_pp = grad_p; q.g_e = prm.g_e;
+            q.N = N; q.T = T; q.S = S; q.Sp = Sp; q.r = pool_ratio; q.eps = eps; q.flags = flags;
+            PooledWs(N, T, Sp).bind(q, workspace);
+            return mma_sparse_run(q, p_dtype, true, st);
         }
         if (p_dense == nullptr || grad_p_dense == nullptr) return SIMULST_E_ARG;
         if (!aligned(p_dense, esz) || !aligned(grad_p_dense, esz)) return SIMULST_E_ALIGN;
@@ -389,29 +429,38 @@ extern "C" {
 
 int simulst_mma_pooled_is_fused(int p_dtype, int S, int ratio, int chunk_size, unsigned flags, int has_mask) {
     if (!valid_dtype(p_dtype) || S <= 0 || S > SIMULST_MMA_MAX_SRC || ratio < 2) return 0;
-    return pooled_fused_shape(p_dtype, S, ratio, chunk_size, flags, has_mask != 0, pick_config(S),
-                              g_use_pipe.load(std::memory_order_relaxed)) ? 1 : 0;
+    return pooled_fused_shape(p_dtype, S, ratio, chunk_size, flags, has_mask != 0) ? 1 : 0;
+}
+
+long long simulst_mma_pooled_workspace_bytes(int N, int T, int S, int ratio) {
+    if (N < 0 || T < 0 || S <= 0 || ratio < 2) return SIMULST_E_SHAPE;
+    return (long long)PooledWs(N, T, (S + ratio - 1) / ratio).total;
+}
+
+int simulst_mma_set_pooled_grid(int enable) {
+    g_pooled_grid.store(enable ? 1 : 0, std::memory_order_relaxed);
+    return SIMULST_OK;
 }
 
 int simulst_mma_train_fwd_pooled(const void* p_pooled, int p_dtype, int ratio, const void* soft_energy, int e_dtype,
                                  const uint8_t* padding_mask, void* p_dense, float* alpha, float* beta, float* side,
-                                 float* expected_delays, int N, int T, int S, float eps, int chunk_size,
-                                 unsigned flags, unsigned* status, void* stream) {
+                                 float* expected_delays, void* workspace, int N, int T, int S, float eps,
+                                 int chunk_size, unsigned flags, unsigned* status, void* stream) {
     if (ratio < 2) return SIMULST_E_ARG;
     return mma_fwd_core(p_pooled, p_dtype, soft_energy, e_dtype, padding_mask, alpha, beta, side, expected_delays,
-                        N, T, S, eps, chunk_size, flags, status, stream, ratio, p_dense);
+                        N, T, S, eps, chunk_size, flags, status, stream, ratio, p_dense, workspace);
 }
 
 int simulst_mma_train_bwd_pooled(const void* p_pooled, int p_dtype, int ratio, const void* soft_energy, int e_dtype,
                                  const uint8_t* padding_mask, const void* p_dense, const float* alpha,
                                  const float* side, const float* grad_alpha, const float* grad_beta,
                                  const float* grad_expected_delays, void* grad_p_pooled, int gp_dtype,
-                                 void* grad_p_dense, void* grad_energy, int ge_dtype, int N, int T, int S,
-                                 float eps, int chunk_size, unsigned flags, void* stream) {
+                                 void* grad_p_dense, void* grad_energy, int ge_dtype, void* workspace,
+                                 int N, int T, int S, float eps, int chunk_size, unsigned flags, void* stream) {
     if (ratio < 2) return SIMULST_E_ARG;
     return mma_bwd_core(p_pooled, p_dtype, soft_energy, e_dtype, padding_mask, alpha, side, grad_alpha, grad_beta,
                         grad_expected_delays, grad_p_pooled, gp_dtype, grad_energy, ge_dtype, N, T, S, eps,
-                        chunk_size, flags, stream, ratio, p_dense, grad_p_dense);
+                        chunk_size, flags, stream, ratio, p_dense, grad_p_dense, workspace);
 }
 
 }  // extern "C"

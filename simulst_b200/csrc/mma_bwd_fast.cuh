@@ -371,14 +371,7 @@ struct FastLayout {
 // each load (p = 0, energy = -inf, grads = 0) -- by one thread-uniform test everywhere except in
 // the single thread the boundary falls into -- their gradients are stored as zeros, and mass
 // preservation follows the reference's right-padding rule (residual ADDED at L_n - 1).
-// POOLED (with RAGGED and DELAYS): prm.p is the POOLED p_choose [N,T,Sp] of the fixed pre-decision
-// wrappers and prm.g_p its gradient [N,T,Sp] (modules/fixed_pre_decision.py:85-95,133-159): the
-// zero-upsampled row is formed in registers from at most two scalars per thread and step (fetched
-// one step ahead), the p row is neither staged nor read densely, and only the gradient entries of
-// the columns that carry a pooled value are stored -- each pooled element owns exactly one column
-// (its natural one, or column S-1 for the last element when S % ratio != 0), so the stores are the
-// whole Jacobian of insert_zeros + slice + last-column assignment.  Requires pool_ratio >= VPT.
-template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED, bool DELAYS, bool MASKED = false, bool POOLED = false>
+template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED, bool DELAYS, bool MASKED = false>
 __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS * VPT <= 2048 ? 2 : 1)))
 mma_bwd_fast_kernel(const MmaParams prm) {
     constexpr int NW = THREADS / kWarp;
@@ -390,7 +383,6 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     constexpr int NS = L::kStages;
     constexpr int NA = L::kAlphaSlots;
     static_assert(NW <= kFastMaxWarps && VPT % 4 == 0, "fast path: at most 16 warps");
-    static_assert(!POOLED || (RAGGED && DELAYS), "pooled rows use the ragged instantiations");
 
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -415,18 +407,7 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     const bool in_row = !RAGGED || j0 < S;              // this thread's VPT columns exist
 
     const size_t row0 = (size_t)n * T_len * S;
-    T* gp_out = reinterpret_cast<T*>(prm.g_p) + (POOLED ? (size_t)n * T_len * prm.Sp : row0);
-    // pooled p_choose: which of this thread's columns carry a pooled value (see mma_fwd_pipe.cuh)
-    int k_nat = -1, k_fix = -1, pn_idx = 0;
-    const T* gpp = nullptr;
-    if constexpr (POOLED) {
-        const int r = prm.pool_ratio;
-        if (j0 < S) {
-            const int jn = ((j0 + r) / r) * r - 1;              // first column >= j0 with (j+1) % r == 0
-            if (jn < j0 + VPT && jn < S) { k_nat = jn - j0; pn_idx = (jn + 1) / r - 1; }
-            if (S % r != 0 && S - 1 >= j0 && S - 1 < j0 + VPT) k_fix = S - 1 - j0;
-        }
-    }
+    T* gp_out = reinterpret_cast<T*>(prm.g_p) + row0;
     T* ge_out = SOFT ? reinterpret_cast<T*>(prm.g_e) + row0 : nullptr;
     // (+ an opaque zero: the compiler must not treat the prefetched side values as uniform, or it
     // converts them to uniform registers -- and waits for the load -- right at the loop top)
@@ -503,7 +484,7 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         for (int w = 0; w < kIssuers; ++w) {
             if (warp == w) {                    // warp-uniform
                 if (elect_one()) {
-                    const bool c_p = !POOLED && (0 % NW) == w, c_e = SOFT && (1 % NW) == w, c_a = (2 % NW) == w,
+                    const bool c_p = (0 % NW) == w, c_e = SOFT && (1 % NW) == w, c_a = (2 % NW) == w,
                                c_ga = (3 % NW) == w, c_gb = SOFT && (4 % NW) == w;      // compile-time
                     const bool a_prev = c_a && i > 0, a_first = c_a && SOFT && q == 0;
                     const bool l_ga = c_ga && has_ga, l_gb = c_gb && has_gb;
@@ -556,13 +537,6 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         side_sum = side[2 * (T_len - 1) + 1];
         if (T_len > 1) side_prev_last = side[2 * (T_len - 2)];
     }
-    float pv_nat = 0.f, pv_fix = 0.f;       // pooled values of the step about to run, fetched one iteration ahead
-    if constexpr (POOLED) {
-        gpp = reinterpret_cast<const T*>(prm.p) + (size_t)n * T_len * prm.Sp;
-        const T* row = gpp + (size_t)(T_len - 1) * prm.Sp;
-        if (k_nat >= 0) pv_nat = to_f32<T>(row[pn_idx]);
-        if (k_fix >= 0) pv_fix = to_f32<T>(row[prm.Sp - 1]);
-    }
     const float* gd_row = nullptr;
     float gd_cur = 0.f;
     if constexpr (DELAYS) {
@@ -598,14 +572,6 @@ mma_bwd_fast_kernel(const MmaParams prm) {
             side_sum_next = ldg_opaque(side + 2 * (i - 1) + 1);
             if (i > 1) side_prev_next = ldg_opaque(side + 2 * (i - 2));
         }
-        unsigned raw_nat_next = 0u, raw_fix_next = 0u;     // raw bits: converted at the end of the iteration
-        if constexpr (POOLED) {
-            if (i > 0) {
-                const T* row = gpp + (size_t)(i - 1) * prm.Sp;
-                if (k_nat >= 0) raw_nat_next = ldg_raw<T>(row + pn_idx);
-                if (k_fix >= 0) raw_fix_next = ldg_raw<T>(row + prm.Sp - 1);
-            }
-        }
         mbar_wait(&bars[s], parity);
         const unsigned char* st = stage0 + s * L::kStage;
         const unsigned char* a_prev_row = alpha0 + a_slot * L::kFRow;                               // alpha'_{i-1}
@@ -614,17 +580,7 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         if (++a_slot == NA) a_slot = 0;
 
         float2 p[H], E[H];
-        if constexpr (POOLED) {
-#pragma unroll
-            for (int q = 0; q < H; ++q) p[q] = f2(0.f);
-#pragma unroll
-            for (int k = 0; k < VPT; ++k) {
-                if (k == k_nat) SIMULST_EL(p, k) = pv_nat;
-                if (k == k_fix) SIMULST_EL(p, k) = pv_fix;
-            }
-        } else {
-            lds_row2<T, VPT>(st + L::kOffP, j0, p);
-        }
+        lds_row2<T, VPT>(st + L::kOffP, j0, p);
         if (SOFT) lds_row2<T, VPT>(st + L::kOffE, j0, E);
         mask_tail(p, 0.f);
         if (SOFT) mask_tail(E, -INFINITY);
@@ -971,16 +927,7 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                 for (int k = 0; k < VPT; ++k)
                     if (k >= nl) outp[k] = 0.f;
             }
-            if constexpr (POOLED) {
-                T* grow = gp_out + (size_t)i * prm.Sp;
-#pragma unroll
-                for (int k = 0; k < VPT; ++k) {
-                    if (k == k_nat) grow[pn_idx] = from_f32<T>(outp[k]);
-                    if (k == k_fix) grow[prm.Sp - 1] = from_f32<T>(outp[k]);
-                }
-            } else {
-                if (MASKED ? in_row : inside) st_row_t<T, VPT, true>(gp_out + (size_t)i * S, j0, S, true, outp);
-            }
+            if (MASKED ? in_row : inside) st_row_t<T, VPT, true>(gp_out + (size_t)i * S, j0, S, true, outp);
         }
         if (SOFT) {
             float oute[VPT];
@@ -1002,14 +949,13 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         side_sum = side_sum_next;
         side_prev_last = side_prev_next;
         if constexpr (DELAYS) gd_cur = gd_next;
-        if constexpr (POOLED) { pv_nat = raw_to_f32<T>(raw_nat_next); pv_fix = raw_to_f32<T>(raw_fix_next); }
     }
 }
 
-template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED, bool DELAYS, bool MASKED = false, bool POOLED = false>
+template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED, bool DELAYS, bool MASKED = false>
 int launch_mma_bwd_fast_impl(const MmaParams& prm, cudaStream_t stream) {
     using L = FastLayout<THREADS * VPT, T, SOFT>;
-    auto kern = mma_bwd_fast_kernel<THREADS, VPT, T, SOFT, RAGGED, DELAYS, MASKED, POOLED>;
+    auto kern = mma_bwd_fast_kernel<THREADS, VPT, T, SOFT, RAGGED, DELAYS, MASKED>;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1044,24 +990,6 @@ int launch_mma_bwd_fast(const MmaParams& prm, cudaStream_t stream) {
         if (prm.S != CAP) return launch_mma_bwd_fast_impl<THREADS, VPT, T, SOFT, true, true>(prm, stream);
         return prm.g_delays != nullptr ? launch_mma_bwd_fast_impl<THREADS, VPT, T, SOFT, false, true>(prm, stream)
                                        : launch_mma_bwd_fast_impl<THREADS, VPT, T, SOFT, false, false>(prm, stream);
-    }
-}
-
-// Pooled p_choose / pooled gradient (prm.pool_ratio > 0).  Returns 1 when the shape does not
-// qualify (the caller then runs the dense kernels on an expanded row and gathers the gradient).
-template <int THREADS, int VPT, typename T, bool SOFT>
-int launch_mma_bwd_fast_pooled(const MmaParams& prm, cudaStream_t stream) {
-    constexpr int CAP = THREADS * VPT;
-    if constexpr (THREADS / kWarp > kFastMaxWarps || VPT % 4 != 0 || VPT > 8 ||
-                  FastLayout<CAP, T, SOFT>::kTotal > 227 * 1024) {
-        return 1;
-    } else {
-        if (!prm.vec_out || !prm.tma || prm.S > CAP || prm.S % VPT != 0 || prm.pool_ratio < VPT ||
-            (prm.flags & SIMULST_MMA_LEFT_PADDING))
-            return 1;
-        if (prm.mask != nullptr)
-            return launch_mma_bwd_fast_impl<THREADS, VPT, T, SOFT, true, true, true, true>(prm, stream);
-        return launch_mma_bwd_fast_impl<THREADS, VPT, T, SOFT, true, true, false, true>(prm, stream);
     }
 }
 

@@ -35,12 +35,6 @@ struct MmaParams {
     int vec_out;            // 1: fp32 rows may be accessed as float4
     int pipe;               // 1: software-pipelined kernels (hard / infinite lookback, needs tma)
     int fast;               // 1: dense fast-path backward kernel when the row qualifies
-    // pooled p_choose (fixed pre-decision): `p` is p_choose_pooled [N,T,Sp]; dense
-    // column j holds pooled[(j+1)/ratio - 1] when (j+1) % ratio == 0, column S-1 holds pooled[Sp-1],
-    // every other column is zero (modules/fixed_pre_decision.py:85-95,133-159)
-    int pool_ratio;         // 0: p is dense
-    int Sp;                 // ceil(S / pool_ratio)
-    void* p_dense;          // fwd, optional: the zero-upsampled [N,T,S] p_choose the reference module returns
     int row_filter;         // masked calls only: 0 all rows, 1 only rows whose mask is a right-padding mask
                             // (j >= len), 2 only the other rows -- the two passes of a masked call
 };

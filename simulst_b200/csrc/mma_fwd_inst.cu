@@ -20,13 +20,6 @@ using InstT = __half;
 int INST_NAME(const MmaParams& prm, int mode, int threads, int vpt, cudaStream_t stream) {
 #define X(TH, VP)                                                                         \
     if (threads == TH && vpt == VP) {                                                     \
-        if (prm.pool_ratio > 0) {               /* pooled p_choose: 1 = expand, then dense */ \
-            if constexpr (TH <= kPipeMaxThreads && VP <= 8) {                             \
-                if (mode == kModeHard) return launch_mma_fwd_pipe_pooled<TH, VP, InstT, false>(prm, stream); \
-                if (mode == kModeSoftIL) return launch_mma_fwd_pipe_pooled<TH, VP, InstT, true>(prm, stream); \
-            }                                                                             \
-            return 1;                                                                     \
-        }                                                                                 \
         if constexpr (TH <= kPipeMaxThreads) {                                            \
             if (prm.tma && prm.pipe && mode != kModeSoftCk) {                             \
                 const int rc = mode == kModeHard ? launch_mma_fwd_pipe<TH, VP, InstT, false>(prm, stream) \

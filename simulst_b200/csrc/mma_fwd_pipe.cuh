@@ -79,20 +79,12 @@ struct PipeStatic {
 // each load (p = 0, energy = -inf) by a test that is thread-uniform except in the one thread
 // the boundary falls into; alpha and beta come out zero there, and mass preservation ADDS its
 // residual at L_n - 1 (monotonic_attention.py:186-193).
-// POOLED (with FULL and RAGGED): prm.p is the POOLED p_choose [N,T,Sp] of the fixed pre-decision
-// wrappers (modules/fixed_pre_decision.py:133-159); the zero-upsampled dense row (insert_zeros
-// :85-95 + the last-column fix-up :156-159) is formed in registers from one or two scalar loads
-// per thread and step, fetched one step ahead -- the p row is never staged, read or (unless
-// prm.p_dense is given) written densely.  Requires pool_ratio >= VPT (at most one pooled column
-// per thread besides the fix-up column).  Same arithmetic as the dense kernel fed the expanded row.
-template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS, bool RAGGED = false, bool MASKED = false,
-          bool POOLED = false>
+template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS, bool RAGGED = false, bool MASKED = false>
 __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS <= 256 ? 2 : 1)))
 mma_fwd_pipe_kernel(const MmaParams prm) {
     using PS = PipeStatic<THREADS, VPT, T, SOFT>;
     constexpr int NW = THREADS / kWarp;
-    constexpr int kIssuers = (SOFT && NW > 1 && !POOLED) ? 2 : 1;     // warps that issue TMA copies
-    static_assert(!POOLED || (FULL && RAGGED), "pooled rows use the dense ragged instantiation");
+    constexpr int kIssuers = (SOFT && NW > 1) ? 2 : 1;     // warps that issue TMA copies
     constexpr int H = VPT / 2;
     static_assert(VPT % 4 == 0, "VPT must be a multiple of 4");
 
@@ -152,18 +144,6 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
         mbar_fence_init();
     }
     const bool inside = !RAGGED || j0 < S;
-    // pooled p_choose: which of this thread's columns carry a pooled value
-    int k_nat = -1, k_fix = -1, pn_idx = 0;
-    const T* gpp = nullptr;
-    if constexpr (POOLED) {
-        const int r = prm.pool_ratio;
-        gpp = reinterpret_cast<const T*>(prm.p) + (size_t)n * T_len * prm.Sp;
-        if (j0 < S) {
-            const int jn = ((j0 + r) / r) * r - 1;              // first column >= j0 with (j+1) % r == 0
-            if (jn < j0 + VPT && jn < S) { k_nat = jn - j0; pn_idx = (jn + 1) / r - 1; }
-            if (S % r != 0 && S - 1 >= j0 && S - 1 < j0 + VPT) k_fix = S - 1 - j0;      // fix-up column (:156-159)
-        }
-    }
     if (RAGGED && !inside) {
         const T ninf = from_f32<T>(-INFINITY), zero = from_f32<T>(0.f);
         for (int s = 0; s < NS; ++s) {
@@ -225,14 +205,7 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
     // one elected lane of warp 0 copies the p row, one of warp 1 (if there is one) the energy
     // row; each arrives on the slot's barrier with its own byte count (warp-uniform branches)
     auto issue = [&](int i, int s) {
-        if constexpr (POOLED) {
-            if (SOFT && warp == 0) {
-                if (elect_one()) {
-                    mbar_expect_tx(&bars[s], row_bytes);
-                    tma_load_1d(stage_e(s), ge + (size_t)i * S, row_bytes, &bars[s]);
-                }
-            }
-        } else if (warp == 0) {
+        if (warp == 0) {
             if (elect_one()) {
                 mbar_expect_tx(&bars[s], (SOFT && kIssuers == 1) ? 2u * row_bytes : row_bytes);
                 tma_load_1d(stage_p(s), gp + (size_t)i * S, row_bytes, &bars[s]);
@@ -272,29 +245,8 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
     unsigned parI = 1u;
     int sb_w = kExStash - 1;                // exp-stash buffer of step it+1 (INV writes it); RECR(it-1) reads the next one
 
-    // pooled p_choose values of the row INV consumes next (row it+1 at iteration it), fetched one
-    // iteration ahead; the first row is loaded here
-    float pv_nat = 0.f, pv_fix = 0.f;
-    unsigned pool_bits = 0u;
-    if constexpr (POOLED) {
-        if (T_len > 0) {
-            if (k_nat >= 0) pv_nat = to_f32<T>(gpp[pn_idx]);
-            if (k_fix >= 0) pv_fix = to_f32<T>(gpp[prm.Sp - 1]);
-        }
-    }
-
     auto body = [&](auto steady_c, const int it) __attribute__((always_inline)) {
         constexpr bool STEADY = decltype(steady_c)::value;
-        // raw bits, converted at the END of the iteration: a conversion here would wait for the
-        // load right away and put the global-load latency on every step's critical path
-        unsigned raw_nat_next = 0u, raw_fix_next = 0u;
-        if constexpr (POOLED) {
-            if (it + 2 >= 1 && it + 2 < T_len) {
-                const T* row = gpp + (size_t)(it + 2) * prm.Sp;
-                if (k_nat >= 0) raw_nat_next = ldg_raw<T>(row + pn_idx);
-                if (k_fix >= 0) raw_fix_next = ldg_raw<T>(row + prm.Sp - 1);
-            }
-        }
         const bool doM = SOFT && (STEADY || it + 2 < T_len);
         const bool doI = STEADY || (it >= -1 && it + 1 < T_len);
         const bool doU = STEADY || (it >= 0 && it < T_len);
@@ -351,27 +303,8 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
         float2 p_n[H], cpre[H], Dl[H];
         float xinc = 1.f, einc = 0.f;
         if (doI) {
-            if (!SOFT && !POOLED) mbar_wait(&bars[slotI], parI);      // with SOFT, MAXS waited for this row one iteration ago
-            if constexpr (POOLED) {
-#pragma unroll
-                for (int q = 0; q < H; ++q) p_n[q] = f2(0.f);
-#pragma unroll
-                for (int k = 0; k < VPT; ++k) {
-                    if (k == k_nat) SIMULST_EL(p_n, k) = pv_nat;
-                    if (k == k_fix) SIMULST_EL(p_n, k) = pv_fix;
-                }
-                if (k_nat >= 0) pool_bits |= prob_bits(pv_nat) | (((1.0f - pv_nat) + eps < 0.f) ? SIMULST_ST_NEGPROD : 0u);
-                if (k_fix >= 0) pool_bits |= prob_bits(pv_fix) | (((1.0f - pv_fix) + eps < 0.f) ? SIMULST_ST_NEGPROD : 0u);
-                if (prm.p_dense != nullptr && inside) {
-                    // the dense p_choose the reference module hands back (fixed_pre_decision.py:139-159)
-                    float pd[VPT];
-#pragma unroll
-                    for (int k = 0; k < VPT; ++k) pd[k] = SIMULST_EL(p_n, k);
-                    st_row_t<T, VPT, true>(reinterpret_cast<T*>(prm.p_dense) + ((size_t)n * T_len + it + 1) * S, j0, S, true, pd);
-                }
-            } else {
-                lds_row2<T, VPT, FULL>(stage_p(slotI) + j0, p_n, umax);
-            }
+            if (!SOFT) mbar_wait(&bars[slotI], parI);      // with SOFT, MAXS waited for this row one iteration ago
+            lds_row2<T, VPT, FULL>(stage_p(slotI) + j0, p_n, umax);
             float2 E_n[H];
             if (SOFT) {
                 unsigned dummy = 0u;
@@ -553,9 +486,6 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
             }
         }
         if (++sb_w == kExStash) sb_w = 0;
-        if constexpr (POOLED) {
-            if (it + 2 >= 1) { pv_nat = raw_to_f32<T>(raw_nat_next); pv_fix = raw_to_f32<T>(raw_fix_next); }
-        }
     };
 
     using Steady = std::integral_constant<bool, true>;
@@ -569,8 +499,7 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
     // ---- data-error reporting (prob_check / safe_cumprod semantics), slow path only on error
     if (prm.status != nullptr) {
         if (nan_out) atomicOr(prm.status, SIMULST_ST_NAN);
-        if (POOLED && pool_bits) atomicOr(prm.status, pool_bits);
-        if (FULL) bad = !POOLED && umax_trips<T>(umax);
+        if (FULL) bad = umax_trips<T>(umax);
         if (bad) {
             unsigned bits = 0u;
             for (int i = 0; i < T_len; ++i)
@@ -587,12 +516,11 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
 
 // ------------------------------------------------------------------ host-side launcher
 // Returns 1 when the row does not fit the pipelined kernel (caller falls back to the generic one).
-template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS, bool RAGGED = false, bool MASKED = false,
-          bool POOLED = false>
+template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS, bool RAGGED = false, bool MASKED = false>
 int launch_mma_fwd_pipe_impl(const MmaParams& prm, cudaStream_t stream) {
     using PS = PipeStatic<THREADS, VPT, T, SOFT>;
     if (!PS::kFits) return 1;
-    auto kern = mma_fwd_pipe_kernel<THREADS, VPT, T, SOFT, FULL, DELAYS, RAGGED, MASKED, POOLED>;
+    auto kern = mma_fwd_pipe_kernel<THREADS, VPT, T, SOFT, FULL, DELAYS, RAGGED, MASKED>;
     static size_t attr_set[64] = {};    // per device: largest dynamic smem size opted into
     int dev = 0;
     cudaGetDevice(&dev);
@@ -622,21 +550,6 @@ int launch_mma_fwd_pipe(const MmaParams& prm, cudaStream_t stream) {
     if (!full) return launch_mma_fwd_pipe_impl<THREADS, VPT, T, SOFT, false, true>(prm, stream);
     return prm.delays != nullptr ? launch_mma_fwd_pipe_impl<THREADS, VPT, T, SOFT, true, true>(prm, stream)
                                  : launch_mma_fwd_pipe_impl<THREADS, VPT, T, SOFT, true, false>(prm, stream);
-}
-
-// Pooled p_choose (prm.pool_ratio > 0).  Returns 1 when the shape does not qualify for the
-// register-expansion path (the caller then expands the row into prm.p_dense and uses the dense
-// kernels): rows must split evenly among the threads, the energy rows must be TMA-legal, the
-// ratio must be >= VPT, and a padding mask is taken as a right-padding mask (the reference's
-// forward() asserts it, monotonic_multihead_attention.py:378-380; the kernel verifies it).
-template <int THREADS, int VPT, typename T, bool SOFT>
-int launch_mma_fwd_pipe_pooled(const MmaParams& prm, cudaStream_t stream) {
-    if (!prm.vec_out || (SOFT && !prm.tma) || prm.S % VPT != 0 || prm.S > THREADS * VPT || prm.pool_ratio < VPT ||
-        (prm.flags & SIMULST_MMA_LEFT_PADDING))
-        return 1;
-    if (prm.mask != nullptr)
-        return launch_mma_fwd_pipe_impl<THREADS, VPT, T, SOFT, true, true, true, true, true>(prm, stream);
-    return launch_mma_fwd_pipe_impl<THREADS, VPT, T, SOFT, true, true, true, false, true>(prm, stream);
 }
 
 }  // namespace simulst

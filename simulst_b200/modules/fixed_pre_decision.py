@@ -29,6 +29,11 @@ class B200FixedStrideMixin(B200MonotonicAttentionMixin):
     # attention dict, :417-421).  Nothing in the reference reads it afterwards; a caller that
     # does not either sets this to False and the [N,T,S] tensor is never written.
     return_dense_p_choose = True
+    # Likewise the dense [N,T,S] alpha: with `with_expected_delays = True` the latency loss reads
+    # the [N,T] delays instead (mma_criterion.py:146-157) and soft attention reaches the output
+    # through beta.  False (with return_dense_p_choose = False, soft attention, a shape the
+    # pooled-grid kernels take): alpha is returned as None and never written.
+    return_dense_alpha = True
     # forward() asserts "Only right padding is supported." (monotonic_multihead_attention.py:378-381);
     # the kernels take that as a promise and VERIFY it per row (a violation poisons the row's
     # outputs with NaN and sets SIMULST_ST_NOT_RIGHT_PADDED).  False: masked calls expand the row
@@ -75,7 +80,8 @@ class B200FixedStrideMixin(B200MonotonicAttentionMixin):
             mass_preservation=self.mass_preservation,
             chunk_size=self.chunk_size if self.soft_attention else None,
             with_delays=bool(getattr(self, "with_expected_delays", False)),
-            want_dense=self.return_dense_p_choose, right_padding=self.assume_right_padding)
+            want_dense=self.return_dense_p_choose, right_padding=self.assume_right_padding,
+            want_alpha=self.return_dense_alpha)
         self.expected_delays = delays
         if not self.soft_attention:
             soft_energy = alpha
@@ -90,7 +96,7 @@ def patch_fixed_pre_decision(cls):
     cls.monotonic_attention_process_train = B200FixedStrideMixin.monotonic_attention_process_train
     cls.monotonic_attention_process_infer = B200MonotonicAttentionMixin.monotonic_attention_process_infer
     cls._alignment = B200MonotonicAttentionMixin._alignment
-    for name in ("return_dense_p_choose", "assume_right_padding"):
+    for name in ("return_dense_p_choose", "return_dense_alpha", "assume_right_padding"):
         if not hasattr(cls, name):
             setattr(cls, name, getattr(B200FixedStrideMixin, name))
     if not hasattr(cls, "expected_delays"):

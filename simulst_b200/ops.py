@@ -155,7 +155,7 @@ class MMATrainPooledFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, p_pooled: Tensor, soft_energy: Optional[Tensor], padding_mask: Optional[Tensor],
                 src_len: int, ratio: int, eps: float, mass_preservation: bool, chunk_size: Optional[int],
-                with_delays: bool, want_dense: bool, right_padding: bool):
+                with_delays: bool, want_dense: bool, right_padding: bool, want_alpha: bool = True):
         lib = _lib.load()
         dev = _lib.require_cuda(p_pooled, soft_energy, padding_mask)
         if p_pooled.dim() != 3:
@@ -190,7 +190,14 @@ class MMATrainPooledFunction(torch.autograd.Function):
                                                      1 if mask is not None else 0))
         need_dense = want_dense or not fused
         p_dense = torch.empty((n, t, s), dtype=p.dtype, device=dev) if need_dense else None
-        alpha = torch.empty((n, t, s), dtype=torch.float32, device=dev)
+        ws = None
+        if fused:       # alpha on the grid + row geometry, carried to the backward call
+            ws = torch.empty(int(lib.simulst_mma_pooled_workspace_bytes(n, t, s, ratio)), dtype=torch.uint8,
+                             device=dev)
+        # the dense alpha can be skipped on the pooled-grid path (soft attention, no dense p_choose):
+        # the caller then reaches alpha through beta and the expected delays only
+        skip_alpha = (not want_alpha) and fused and soft and not need_dense
+        alpha = None if skip_alpha else torch.empty((n, t, s), dtype=torch.float32, device=dev)
         beta = torch.empty((n, t, s), dtype=torch.float32, device=dev) if soft else None
         small = torch.zeros if mask is not None else torch.empty
         side = small((n, t, 2), dtype=torch.float32, device=dev) if mass_preservation else None
@@ -200,28 +207,29 @@ class MMATrainPooledFunction(torch.autograd.Function):
             rc = lib.simulst_mma_train_fwd_pooled(
                 _lib.ptr(p), _lib.dtype_enum(p.dtype), ratio, _lib.ptr(e),
                 _lib.dtype_enum(e.dtype) if soft else 0, _lib.ptr(mask), _lib.ptr(p_dense),
-                _lib.ptr(alpha), _lib.ptr(beta), _lib.ptr(side), _lib.ptr(delays),
+                _lib.ptr(alpha), _lib.ptr(beta), _lib.ptr(side), _lib.ptr(delays), _lib.ptr(ws),
                 n, t, s, float(eps), chunk, flags, _lib.ptr(status), _lib.stream_ptr(dev))
         _lib.check(rc, "simulst_mma_train_fwd_pooled")
         _lib.maybe_check(dev)
-        ctx.save_for_backward(p, e, mask, alpha, side, None if fused else p_dense)
+        ctx.save_for_backward(p, e, mask, alpha, side, None if fused else p_dense, ws)
         ctx.cfg = (n, t, s, ratio, float(eps), chunk, flags, soft, fused)
         ctx.in_dtypes = (p_pooled.dtype, soft_energy.dtype if soft else None)
         ctx.set_materialize_grads(False)
-        out_dense = p_dense if want_dense else alpha.new_empty(0)
+        empty = p.new_empty(0, dtype=torch.float32)
+        out_dense = p_dense if want_dense else empty.to(p_pooled.dtype)
         if out_dense.dtype != p_pooled.dtype:
             out_dense = out_dense.to(p_pooled.dtype)
         ctx.mark_non_differentiable(out_dense)
-        return (alpha, beta if soft else alpha.new_empty(0),
-                delays if with_delays else alpha.new_empty(0), out_dense)
+        return (alpha if alpha is not None else empty.clone(), beta if soft else empty.clone(),
+                delays if with_delays else empty.clone(), out_dense)
 
     @staticmethod
     def backward(ctx, g_alpha, g_beta, g_delays, _g_dense):
         lib = _lib.load()
-        p, e, mask, alpha, side, p_dense = ctx.saved_tensors
+        p, e, mask, alpha, side, p_dense, ws = ctx.saved_tensors
         n, t, s, ratio, eps, chunk, flags, soft, fused = ctx.cfg
         dev = p.device
-        ga = g_alpha.contiguous().float() if g_alpha is not None else None
+        ga = g_alpha.contiguous().float() if (g_alpha is not None and g_alpha.numel() == n * t * s) else None
         gb = g_beta.contiguous().float() if (soft and g_beta is not None) else None
         gd = g_delays.contiguous().float() if (g_delays is not None and g_delays.numel() == n * t) else None
         grad_p = torch.empty_like(p)
@@ -233,7 +241,7 @@ class MMATrainPooledFunction(torch.autograd.Function):
                 _lib.dtype_enum(e.dtype) if soft else 0, _lib.ptr(mask), _lib.ptr(p_dense),
                 _lib.ptr(alpha), _lib.ptr(side), _lib.ptr(ga), _lib.ptr(gb), _lib.ptr(gd),
                 _lib.ptr(grad_p), _lib.dtype_enum(p.dtype), _lib.ptr(grad_dense), _lib.ptr(grad_e),
-                _lib.dtype_enum(e.dtype) if soft else 0,
+                _lib.dtype_enum(e.dtype) if soft else 0, _lib.ptr(ws),
                 n, t, s, eps, chunk, flags, _lib.stream_ptr(dev))
         _lib.check(rc, "simulst_mma_train_bwd_pooled")
         p_dt, e_dt = ctx.in_dtypes
@@ -241,23 +249,29 @@ class MMATrainPooledFunction(torch.autograd.Function):
             grad_p = grad_p.to(p_dt)
         if soft and grad_e.dtype != e_dt:
             grad_e = grad_e.to(e_dt)
-        return (grad_p, grad_e) + (None,) * 9
+        return (grad_p, grad_e) + (None,) * 10
 
 
 def mma_train_pooled(p_choose_pooled: Tensor, src_len: int, ratio: int,
                      soft_energy: Optional[Tensor] = None, padding_mask: Optional[Tensor] = None,
                      eps: float = 1e-6, mass_preservation: bool = True, chunk_size: Optional[int] = None,
-                     with_delays: bool = False, want_dense: bool = True, right_padding: bool = False):
+                     with_delays: bool = False, want_dense: bool = True, right_padding: bool = False,
+                     want_alpha: bool = True):
     """Fixed pre-decision training path from the POOLED p_choose.
     Returns (p_choose [N,T,S] or None, alpha, beta, expected_delays or None); beta is alpha for hard
     attention.  ``right_padding=True`` is the caller's promise that ``padding_mask`` is a
     right-padding mask (verified on the device: a violation poisons the outputs with NaN and sets
-    SIMULST_ST_NOT_RIGHT_PADDED); without it a masked call expands the row and runs the dense path."""
+    SIMULST_ST_NOT_RIGHT_PADDED); without it a masked call expands the row and runs the dense path.
+    ``want_alpha=False`` (with ``want_dense=False``, soft attention, a shape the pooled-grid kernels
+    take) skips the dense [N,T,S] alpha: alpha then reaches the caller through beta and the expected
+    delays only, which is all MMACriterion uses it for (mma_criterion.py:146-157)."""
     alpha, beta, delays, dense = MMATrainPooledFunction.apply(
         p_choose_pooled, soft_energy, padding_mask, src_len, ratio, eps, mass_preservation, chunk_size,
-        with_delays, want_dense, right_padding)
+        with_delays, want_dense, right_padding, want_alpha)
     if soft_energy is None:
         beta = alpha
+    if alpha.numel() == 0 and p_choose_pooled.numel() != 0:
+        alpha = None        # want_alpha=False on the pooled-grid path: the dense alpha was never written
     return (dense if want_dense else None), alpha, beta, (delays if with_delays else None)
 
 

@@ -79,8 +79,10 @@ def _seeded(n, t, s, ratio, seed, masked):
     (2, 32, 2048, 8, False, True, torch.float32),        # 256-thread CTAs
     (1, 16, 4096, 16, True, True, torch.float32),        # 512-thread CTAs
     (2, 16, 999, 8, False, True, torch.float32),         # rows not 16-byte multiples: expanded, dense path
-    (2, 16, 1024, 4, False, True, torch.float32),        # ratio below the per-thread element count: expanded
-    (1, 8, 6000, 8, False, True, torch.float32),         # long rows (12 elements per thread): expanded
+    (2, 16, 1024, 4, False, True, torch.float32),        # ratio 4: two grid columns per thread
+    (2, 16, 1024, 3, True, True, torch.float32),         # ratio 3: grid columns at uneven thread offsets
+    (3, 9, 520, 16, True, False, torch.float32),         # hard-aligned, ratio 16, residual off the grid
+    (1, 8, 6000, 8, False, True, torch.float32),         # rows beyond 4096 frames: expanded
     (2, 24, 512, 8, False, True, torch.float32),         # chunkwise: expanded (run with chunk below)
 ])
 def test_pooled_training_path_matches_oracle(n, t, s, ratio, masked, soft, dtype):
@@ -118,14 +120,21 @@ def test_pooled_training_path_matches_oracle(n, t, s, ratio, masked, soft, dtype
 
 
 @pytest.mark.parametrize("s,masked", [(1024, False), (1000, True), (264, True)])
-def test_pooled_equals_dense_kernels_on_the_expanded_row(s, masked):
-    """Same arithmetic, only the load differs: outputs and gradients bit-identical to the dense
-    entry points fed the zero-upsampled tensor (which is also what the non-fused shapes run)."""
+def test_pooled_grid_kernels_agree_with_dense_kernels_on_the_expanded_row(s, masked):
+    """The pooled-grid path (mma_sparse.cu) against the dense kernels fed the zero-upsampled tensor
+    -- and the expand + dense route of the pooled entry points (simulst_mma_set_pooled_grid(0)),
+    which must agree with the dense entry points bit for bit."""
     import simulst_b200
-    from simulst_b200 import ops
+    from simulst_b200 import _lib, ops
+    lib = _lib.load()
     n, t, ratio = 3, 20, 8
     pp, se, ga, gb, mask = _seeded(n, t, s, ratio, 77, masked)
     dense, alpha, beta, gpp, gse = _run(pp, s, ratio, se, mask, True, ga, gb, right_padding=masked)
+    lib.simulst_mma_set_pooled_grid(0)
+    try:
+        dense_x, alpha_x, beta_x, gpp_x, gse_x = _run(pp, s, ratio, se, mask, True, ga, gb, right_padding=masked)
+    finally:
+        lib.simulst_mma_set_pooled_grid(1)
     simulst_b200.assume_right_padding(masked)
     try:
         pd = dense.detach().clone().requires_grad_()
@@ -134,11 +143,16 @@ def test_pooled_equals_dense_kernels_on_the_expanded_row(s, masked):
         ((a2 * ga.to(DEV)).sum() + (b2 * gb.to(DEV)).sum()).backward()
     finally:
         simulst_b200.assume_right_padding(False)
-    assert torch.equal(alpha, a2) and torch.equal(beta, b2)
-    assert torch.equal(gse, sed.grad)
     cols = torch.arange(1, pp.shape[-1] + 1) * ratio - 1
     cols[-1] = s - 1
-    assert torch.equal(gpp, pd.grad[:, :, cols.to(DEV)])
+    assert torch.equal(dense, dense_x)
+    assert torch.equal(alpha_x, a2) and torch.equal(beta_x, b2) and torch.equal(gse_x, sed.grad)
+    assert torch.equal(gpp_x, pd.grad[:, :, cols.to(DEV)])
+    floor = 4e-7 * s * float(max(ga.abs().max(), gb.abs().max()))
+    assert_parity(alpha, a2, "grid vs dense alpha")
+    assert_parity(beta, b2, "grid vs dense beta")
+    assert_parity(gse, sed.grad, "grid vs dense grad_energy", extra_atol=floor)
+    assert_parity(gpp, gpp_x, "grid vs dense grad_p_pooled", extra_atol=floor)
 
 
 def test_pooled_without_dense_output_and_is_fused_query():
@@ -157,7 +171,8 @@ def test_pooled_without_dense_output_and_is_fused_query():
     a = torch.empty(2, 6, 999, device=DEV)
     p = torch.rand(2, 6, 125, device=DEV)
     rc = lib.simulst_mma_train_fwd_pooled(_lib.ptr(p), _lib.F32, 8, None, 0, None, None, _lib.ptr(a), None, None,
-                                          None, 2, 6, 999, 1e-6, 0, 0, None, _lib.stream_ptr(torch.device(DEV)))
+                                          None, None, 2, 6, 999, 1e-6, 0, 0, None,
+                                          _lib.stream_ptr(torch.device(DEV)))
     assert rc == -1
 
 
