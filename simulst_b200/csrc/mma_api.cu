@@ -31,10 +31,9 @@ static Config pick_config(int S) {
     if (forced != 0 && (forced >> 8) * (forced & 255) >= S) return {forced >> 8, forced & 255};
     if (S <= 128) return {32, 4};
     if (S <= 256) return {32, 8};
-    if (S <= 512) return {64, 8};
-    if (S <= 1024) return {128, 8};
-    if (S <= 2048) return {256, 8};
-    if (S <= 4096) return {512, 8};
+    if (S <= 1024) return {(S + 255) / 256 * 32, 8};            // 64, 96, 128 threads
+    if (S <= 2048) return {(S + 255) / 256 * 32, 8};            // 160 .. 256 threads
+    if (S <= 4096) return {(S + 511) / 512 * 64, 8};            // 320 .. 512 threads
     if (S <= 6144) return {512, 12};
     if (S <= 8192) return {512, 16};
     return {1024, 16};
@@ -237,6 +236,7 @@ int mma_fwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
     const int use_pipe = g_use_pipe.load(std::memory_order_relaxed);
     prm.tma = g_use_tma.load(std::memory_order_relaxed) && ((size_t)S * esz) % 16 == 0 &&
               (pool_ratio > 0 || aligned(p_choose, 16)) && (!soft || aligned(soft_energy, 16));
+    prm.tma_shift = g_use_tma.load(std::memory_order_relaxed) && !prm.tma;
     prm.vec_out = (S % 4 == 0) && aligned(alpha, 16) && (!soft || aligned(beta, 16));
     prm.pipe = use_pipe & 1;
 
@@ -275,6 +275,7 @@ int mma_fwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
         if (xrc != SIMULST_OK) return xrc;
         prm.p = p_dense;
         prm.tma = prm.tma && aligned(p_dense, 16);
+        prm.tma_shift = g_use_tma.load(std::memory_order_relaxed) && !prm.tma;
     }
     if (split_masked_call(prm, mode, cfg, prm.pipe != 0)) {
         // pass 1: rows whose mask is a right-padding mask, through the dense kernels;
@@ -365,6 +366,7 @@ int mma_bwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
                      (!soft || aligned(grad_energy, 16));
     const int use_pipe = g_use_pipe.load(std::memory_order_relaxed);
     prm.tma = g_use_tma.load(std::memory_order_relaxed) && ((size_t)S * esz) % 16 == 0 && a16;
+    prm.tma_shift = g_use_tma.load(std::memory_order_relaxed) && !prm.tma;
     prm.vec_out = ((size_t)S * esz) % 16 == 0 && (S % 4 == 0) && a16;
     prm.pipe = (use_pipe >> 1) & 1;
     prm.fast = (use_pipe >> 2) & 1;
@@ -401,6 +403,7 @@ int mma_bwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
         prm.p = p_dense; prm.g_p = grad_p_dense;
         const bool d16 = aligned(p_dense, 16) && aligned(grad_p_dense, 16);
         prm.tma = prm.tma && d16;
+        prm.tma_shift = g_use_tma.load(std::memory_order_relaxed) && !prm.tma;
         prm.vec_out = prm.vec_out && d16;
         gather = true;
     }

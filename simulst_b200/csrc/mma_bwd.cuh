@@ -133,6 +133,23 @@ __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : 1)) mma_
                 if (has_ga) tma_load_1d(st_ptr(s, plan.off_ga), gA_in + (size_t)i * S, f_bytes, &bars[s]);
                 if (has_gb) tma_load_1d(st_ptr(s, plan.off_gb), gB_in + (size_t)i * S, f_bytes, &bars[s]);
             }
+        } else if (prm.tma_shift) {
+            if (tid == 0) {
+                // 16-byte aligned supersets of the (unaligned) rows; see tma_span
+                unsigned nb[5] = {0u, 0u, 0u, 0u, 0u};
+                const void* src[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+                src[0] = tma_span(gp_in + (size_t)i * S, t_bytes, nb[0]);
+                if (SOFT) src[1] = tma_span(ge_in + (size_t)i * S, t_bytes, nb[1]);
+                if (i > 0) src[2] = tma_span(al + (size_t)(i - 1) * S, f_bytes, nb[2]);
+                if (has_ga) src[3] = tma_span(gA_in + (size_t)i * S, f_bytes, nb[3]);
+                if (has_gb) src[4] = tma_span(gB_in + (size_t)i * S, f_bytes, nb[4]);
+                mbar_expect_tx(&bars[s], nb[0] + nb[1] + nb[2] + nb[3] + nb[4]);
+                tma_load_1d(st_ptr(s, plan.off_p), src[0], nb[0], &bars[s]);
+                if (SOFT) tma_load_1d(st_ptr(s, plan.off_e), src[1], nb[1], &bars[s]);
+                if (i > 0) tma_load_1d(st_ptr(s, plan.off_a), src[2], nb[2], &bars[s]);
+                if (has_ga) tma_load_1d(st_ptr(s, plan.off_ga), src[3], nb[3], &bars[s]);
+                if (has_gb) tma_load_1d(st_ptr(s, plan.off_gb), src[4], nb[4], &bars[s]);
+            }
         } else {
             coop(st_ptr(s, plan.off_p), gp_in + (size_t)i * S, sizeof(T));
             if (SOFT) coop(st_ptr(s, plan.off_e), ge_in + (size_t)i * S, sizeof(T));
@@ -142,7 +159,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : 1)) mma_
         }
     };
     for (int q = 0; q < NS - 1 && q < T_len; ++q) issue(q, q);
-    if (!prm.tma) __syncthreads();
+    const bool use_tma = prm.tma || prm.tma_shift;
+    if (!use_tma) __syncthreads();
 
     const float one_eps = 1.0f + eps;
     float carry[VPT], a_cur[VPT];
@@ -162,19 +180,25 @@ __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : 1)) mma_
             if (i > 0) side_prev_last = side[2 * (i - 1)];
         }
         const float gd = has_gd ? prm.g_delays[(size_t)n * T_len + i] : 0.f;
-        if (prm.tma) mbar_wait(&bars[s], parity);
+        if (use_tma) mbar_wait(&bars[s], parity);
 
         float p[VPT], E[VPT], am1[VPT], gA[VPT], gB[VPT];
-        lds_row<T, VPT>(reinterpret_cast<const T*>(st_ptr(s, plan.off_p)), j0, p);
-        if (SOFT) lds_row<T, VPT>(reinterpret_cast<const T*>(st_ptr(s, plan.off_e)), j0, E);
+        const bool shifted = prm.tma_shift != 0;
+        lds_row_shift<T, VPT>(reinterpret_cast<const T*>(st_ptr(s, plan.off_p)),
+                              shifted ? row_shift(gp_in + (size_t)i * S) : 0, j0, p);
+        if (SOFT) lds_row_shift<T, VPT>(reinterpret_cast<const T*>(st_ptr(s, plan.off_e)),
+                                        shifted ? row_shift(ge_in + (size_t)i * S) : 0, j0, E);
         if (i > 0) {
-            lds_row<float, VPT>(reinterpret_cast<const float*>(st_ptr(s, plan.off_a)), j0, am1);
+            lds_row_shift<float, VPT>(reinterpret_cast<const float*>(st_ptr(s, plan.off_a)),
+                                      shifted ? row_shift(al + (size_t)(i - 1) * S) : 0, j0, am1);
         } else {
 #pragma unroll
             for (int k = 0; k < VPT; ++k) am1[k] = (j0 + k == 0) ? 1.0f : 0.0f;
         }
-        if (has_ga) lds_row<float, VPT>(reinterpret_cast<const float*>(st_ptr(s, plan.off_ga)), j0, gA);
-        if (has_gb) lds_row<float, VPT>(reinterpret_cast<const float*>(st_ptr(s, plan.off_gb)), j0, gB);
+        if (has_ga) lds_row_shift<float, VPT>(reinterpret_cast<const float*>(st_ptr(s, plan.off_ga)),
+                                              shifted ? row_shift(gA_in + (size_t)i * S) : 0, j0, gA);
+        if (has_gb) lds_row_shift<float, VPT>(reinterpret_cast<const float*>(st_ptr(s, plan.off_gb)),
+                                              shifted ? row_shift(gB_in + (size_t)i * S) : 0, j0, gB);
         if (++s == NS) { s = 0; parity ^= 1u; }
         if (++s_fill == NS) s_fill = 0;
         float a_save[VPT];          // alpha'_{i-1} exactly as stored (becomes a_cur next step)
@@ -536,8 +560,8 @@ int launch_mma_bwd_impl(const MmaParams& prm, cudaStream_t stream) {
     constexpr int CAP = THREADS * VPT;
     const bool soft = MODE != kModeHard;
     BwdPlan plan;
-    const int t_row = (CAP * (int)sizeof(T) + 127) / 128 * 128;
-    const int f_row = (CAP * 4 + 127) / 128 * 128;
+    const int t_row = (CAP * (int)sizeof(T) + 16 + 127) / 128 * 128;      // + the head of a shifted row
+    const int f_row = (CAP * 4 + 16 + 127) / 128 * 128;
     int off = 0;
     plan.off_p = off; off += t_row;
     plan.off_e = off; if (soft) off += t_row;

@@ -153,10 +153,14 @@ __device__ __forceinline__ void load_totals(const float* __restrict__ wt, float 
         const float2 v = *reinterpret_cast<const float2*>(wt);
         t[0] = v.x; t[1] = v.y;
     } else {
+        // (a slot holds kXStride floats, so the last vector may reach past NW; the extra lanes are dropped)
 #pragma unroll
-        for (int q = 0; q < NW / 4; ++q) {
+        for (int q = 0; q < (NW + 3) / 4; ++q) {
             const float4 v = *reinterpret_cast<const float4*>(wt + 4 * q);
-            t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+            if (4 * q < NW) t[4 * q] = v.x;
+            if (4 * q + 1 < NW) t[4 * q + 1] = v.y;
+            if (4 * q + 2 < NW) t[4 * q + 2] = v.z;
+            if (4 * q + 3 < NW) t[4 * q + 3] = v.w;
         }
     }
 }
@@ -372,7 +376,7 @@ struct FastLayout {
 // the single thread the boundary falls into -- their gradients are stored as zeros, and mass
 // preservation follows the reference's right-padding rule (residual ADDED at L_n - 1).
 template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED, bool DELAYS, bool MASKED = false>
-__global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS * VPT <= 2048 ? 2 : 1)))
+__global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS <= 160 ? 3 : (THREADS <= 256 ? 2 : 1))))
 mma_bwd_fast_kernel(const MmaParams prm) {
     constexpr int NW = THREADS / kWarp;
     constexpr int H = VPT / 2;

@@ -35,6 +35,8 @@ struct MmaParams {
     int vec_out;            // 1: fp32 rows may be accessed as float4
     int pipe;               // 1: software-pipelined kernels (hard / infinite lookback, needs tma)
     int fast;               // 1: dense fast-path backward kernel when the row qualifies
+    int tma_shift;          // 1 (generic kernels only): rows are not 16-byte multiples; a bulk copy fetches the
+                            // 16-byte aligned superset of a row and the consumer reads at the row's offset in it
     int row_filter;         // masked calls only: 0 all rows, 1 only rows whose mask is a right-padding mask
                             // (j >= len), 2 only the other rows -- the two passes of a masked call
 };
@@ -84,6 +86,30 @@ __device__ __forceinline__ void lds_row(const T* __restrict__ row, int j0, float
         Pack<T, PK> pk = *reinterpret_cast<const Pack<T, PK>*>(row + j0 + q * PK);
 #pragma unroll
         for (int k = 0; k < PK; ++k) out[q * PK + k] = to_f32<T>(pk.v[k]);
+    }
+}
+
+// Rows that are not 16-byte multiples (generic kernels, prm.tma_shift): the bulk copy covers the
+// 16-byte aligned superset [row & ~15, roundup16(row + bytes)) -- every 16-byte granule that holds a
+// valid byte of an allocation is mapped, so the over-read never faults -- and the row starts
+// `shift` elements into the staged copy.
+__device__ __forceinline__ const void* tma_span(const void* row, unsigned bytes, unsigned& span_bytes) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(row), a0 = a & ~static_cast<uintptr_t>(15);
+    span_bytes = (static_cast<unsigned>(a - a0) + bytes + 15u) & ~15u;
+    return reinterpret_cast<const void*>(a0);
+}
+template <typename T>
+__device__ __forceinline__ int row_shift(const T* row) {
+    return static_cast<int>((reinterpret_cast<uintptr_t>(row) & 15u) / sizeof(T));
+}
+// lds_row of a staged row that starts `shift` elements into its slot (scalar reads when shift != 0)
+template <typename T, int VPT>
+__device__ __forceinline__ void lds_row_shift(const T* __restrict__ row, int shift, int j0, float (&out)[VPT]) {
+    if (shift == 0) {
+        lds_row<T, VPT>(row, j0, out);
+    } else {
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) out[k] = to_f32<T>(row[shift + j0 + k]);
     }
 }
 

@@ -95,12 +95,22 @@ __global__ void __launch_bounds__(THREADS) mma_fwd_kernel(const MmaParams prm, c
     const unsigned row_bytes = (unsigned)(S * sizeof(T));
     auto stage_p = [&](int s) { return reinterpret_cast<T*>(stage0 + (size_t)(s * plan.rows) * plan.row_bytes); };
     auto stage_e = [&](int s) { return reinterpret_cast<T*>(stage0 + (size_t)(s * plan.rows + 1) * plan.row_bytes); };
+    const bool use_tma = prm.tma || prm.tma_shift;
     auto issue = [&](int i, int s) {
         if (prm.tma) {
             if (tid == 0) {
                 mbar_expect_tx(&bars[s], SOFT ? 2u * row_bytes : row_bytes);
                 tma_load_1d(stage_p(s), gp + (size_t)i * S, row_bytes, &bars[s]);
                 if (SOFT) tma_load_1d(stage_e(s), ge + (size_t)i * S, row_bytes, &bars[s]);
+            }
+        } else if (prm.tma_shift) {
+            if (tid == 0) {
+                unsigned np = 0u, ne = 0u;
+                const void* sp = tma_span(gp + (size_t)i * S, row_bytes, np);
+                const void* se = SOFT ? tma_span(ge + (size_t)i * S, row_bytes, ne) : nullptr;
+                mbar_expect_tx(&bars[s], np + ne);
+                tma_load_1d(stage_p(s), sp, np, &bars[s]);
+                if (SOFT) tma_load_1d(stage_e(s), se, ne, &bars[s]);
             }
         } else {
             T* dp = stage_p(s);
@@ -118,7 +128,7 @@ __global__ void __launch_bounds__(THREADS) mma_fwd_kernel(const MmaParams prm, c
 #pragma unroll
     for (int i = 0; i < NS - 1; ++i)
         if (i < T_len) issue(i, i);
-    if (!prm.tma) __syncthreads();
+    if (!use_tma) __syncthreads();
 
     const float one_eps = 1.0f + eps;       // first element of the exclusive cumprod (functions.py:28-33)
     float a_prev[VPT];
@@ -133,11 +143,16 @@ __global__ void __launch_bounds__(THREADS) mma_fwd_kernel(const MmaParams prm, c
     for (int i = 0; i < T_len; ++i) {
         // refill the slot consumed in the previous step (every thread passed >= 1 barrier since)
         if (i + NS - 1 < T_len) issue(i + NS - 1, s_fill);
-        if (prm.tma) mbar_wait(&bars[s], parity);
+        if (use_tma) mbar_wait(&bars[s], parity);
 
         float p[VPT], E[VPT];
-        lds_row<T, VPT>(stage_p(s), j0, p);
-        if (SOFT) lds_row<T, VPT>(stage_e(s), j0, E);
+        if (prm.tma_shift) {
+            lds_row_shift<T, VPT>(stage_p(s), row_shift(gp + (size_t)i * S), j0, p);
+            if (SOFT) lds_row_shift<T, VPT>(stage_e(s), row_shift(ge + (size_t)i * S), j0, E);
+        } else {
+            lds_row<T, VPT>(stage_p(s), j0, p);
+            if (SOFT) lds_row<T, VPT>(stage_e(s), j0, E);
+        }
         if (++s == NS) { s = 0; parity ^= 1u; }
         if (++s_fill == NS) s_fill = 0;
 
@@ -374,7 +389,7 @@ template <int THREADS, int VPT, typename T, int MODE, bool FULL>
 int launch_mma_fwd_impl(const MmaParams& prm, cudaStream_t stream) {
     StagePlan plan;
     plan.rows = (MODE == kModeHard) ? 1 : 2;
-    plan.row_bytes = ((THREADS * VPT * (int)sizeof(T)) + 127) / 128 * 128;
+    plan.row_bytes = ((THREADS * VPT * (int)sizeof(T)) + 16 + 127) / 128 * 128;    // + the head of a shifted row
     plan.win_floats = (MODE == kModeSoftCk) ? THREADS * VPT : 0;
     plan.n_stage = kFwdStages;
     auto kern = mma_fwd_kernel<THREADS, VPT, T, MODE, FULL>;

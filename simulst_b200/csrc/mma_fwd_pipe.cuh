@@ -80,7 +80,7 @@ struct PipeStatic {
 // the boundary falls into; alpha and beta come out zero there, and mass preservation ADDS its
 // residual at L_n - 1 (monotonic_attention.py:186-193).
 template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS, bool RAGGED = false, bool MASKED = false>
-__global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS <= 256 ? 2 : 1)))
+__global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS <= 160 ? 3 : (THREADS <= 256 ? 2 : 1))))
 mma_fwd_pipe_kernel(const MmaParams prm) {
     using PS = PipeStatic<THREADS, VPT, T, SOFT>;
     constexpr int NW = THREADS / kWarp;

@@ -23,6 +23,15 @@ HEADLINE = [
     (1, 256, 6000, torch.float32),       # config 5: longest rows
     (2, 128, 1500, torch.bfloat16),      # S*2 bytes not a multiple of 16 (the CIF config's own S)
     (2, 64, 1504, torch.float32),        # S between two CTA sizes
+    # CTA sizes in one-warp steps (csrc/mma_dispatch.h): 96, 160, 192, 224, 320, 384, 448 threads
+    (2, 24, 768, torch.bfloat16),
+    (2, 24, 1280, torch.float32),
+    (2, 24, 1536, torch.bfloat16),
+    (2, 24, 1792, torch.float32),
+    (2, 16, 2560, torch.bfloat16),
+    (2, 16, 3000, torch.float32),        # ragged inside a 384-thread CTA
+    (2, 16, 3584, torch.bfloat16),
+    (3, 16, 600, torch.float32),         # ragged inside a 96-thread CTA
 ]
 
 

@@ -155,6 +155,35 @@ def test_pooled_grid_kernels_agree_with_dense_kernels_on_the_expanded_row(s, mas
     assert_parity(gpp, gpp_x, "grid vs dense grad_p_pooled", extra_atol=floor)
 
 
+@pytest.mark.parametrize("s,masked", [(1024, False), (520, True)])
+def test_pooled_latency_loss_mode_without_dense_alpha(s, masked):
+    """want_alpha=False: the dense alpha is never written; alpha reaches the loss through beta and the
+    expected delays only (mma_criterion.py:146-157).  Outputs and gradients against the oracle, which
+    forms the delays from its dense alpha."""
+    import simulst_b200
+    from simulst_b200 import ops
+    n, t, ratio = 3, 24, 8
+    pp, se, _, gb, mask = _seeded(n, t, s, ratio, 91, masked)
+    g = torch.Generator().manual_seed(92)
+    gd = torch.randn(n, t, generator=g) / s
+    ppd, sed = pp.to(DEV).requires_grad_(), se.to(DEV).requires_grad_()
+    dense, alpha, beta, delays = ops.mma_train_pooled(ppd, s, ratio, sed, mask.to(DEV) if masked else None,
+                                                      with_delays=True, want_dense=False, right_padding=masked,
+                                                      want_alpha=False)
+    assert dense is None and alpha is None
+    ((beta * gb.to(DEV)).sum() + (delays * gd.to(DEV)).sum()).backward()
+    simulst_b200.check_status()
+    ppo, seo = pp.clone().requires_grad_(), se.clone().requires_grad_()
+    _, a_o, b_o = omma.mma_process_train_pooled(ppo, s, ratio, seo, mask, 1e-6, True, None)
+    d_o = omma.expected_delays(a_o)
+    ((b_o * gb).sum() + (d_o * gd).sum()).backward()
+    assert_parity(beta, b_o, "lean beta")
+    assert_parity(delays, d_o, "lean delays", extra_atol=2e-6 * s)
+    floor = 4e-7 * s * float(max(gb.abs().max(), (gd.abs().max() * s)))
+    assert_parity(ppd.grad, ppo.grad, "lean grad_p_pooled", extra_atol=floor)
+    assert_parity(sed.grad, seo.grad, "lean grad_energy", extra_atol=floor)
+
+
 def test_pooled_without_dense_output_and_is_fused_query():
     from simulst_b200 import _lib, ops
     lib = _lib.load()
