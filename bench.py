@@ -273,6 +273,37 @@ def run_ours(args):
     ge_host = torch.empty(N_ROWS, T, S, dtype=dt).pin_memory()
     status = _lib.status_word(dev)
     grad_buf = torch.randn(GRAD_BUF_ELEMS, device=dev)
+    # Gradient all-reduce: NVSwitch multicast kernel (simulst_multimem_allreduce_f32, a few CTAs) on a
+    # symmetric buffer when the box supports it, NCCL otherwise (SIMULST_ALLREDUCE=nccl forces NCCL).
+    mm = None
+    mm_note = None
+    if world > 1 and os.environ.get("SIMULST_ALLREDUCE", "multimem") == "multimem":
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            buf = symm_mem.empty(GRAD_BUF_ELEMS, dtype=torch.float32, device=dev)
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+            if not hdl.multicast_ptr:
+                raise RuntimeError("no multicast mapping")
+            mm = {"hdl": hdl, "ptr": int(hdl.multicast_ptr), "stream": torch.cuda.Stream(),
+                  "ev": torch.cuda.Event(), "ctas": int(os.environ.get("SIMULST_ALLREDUCE_CTAS", "2"))}
+            grad_buf = buf
+            # known-answer check of the kernel: every rank holds rank+1 -> the sum everywhere
+            grad_buf.fill_(float(rank + 1))
+            torch.cuda.synchronize()
+            hdl.barrier(channel=0)
+            _lib.check(lib.simulst_multimem_allreduce_f32(mm["ptr"], GRAD_BUF_ELEMS, rank, world, mm["ctas"],
+                                                          torch.cuda.current_stream().cuda_stream),
+                       "simulst_multimem_allreduce_f32")
+            hdl.barrier(channel=1)
+            torch.cuda.synchronize()
+            want = world * (world + 1) / 2.0
+            if not bool((grad_buf == want).all()):
+                raise RuntimeError(f"multimem all-reduce check failed: {float(grad_buf.min())}..{float(grad_buf.max())} != {want}")
+            grad_buf.normal_()
+        except Exception as exc:
+            mm = None
+            mm_note = repr(exc)
+            grad_buf = torch.randn(GRAD_BUF_ELEMS, device=dev)
     stream = torch.cuda.current_stream()
     st = stream.cuda_stream
     flags = _lib.MMA_MASS_PRESERVATION | _lib.MMA_SOFT
@@ -302,9 +333,33 @@ def run_ours(args):
         if timers is not None:
             timers[2].record(stream)
         if world > 1:
-            if pending[0] is not None:
-                pending[0].wait()
-            pending[0] = dist.all_reduce(grad_buf, async_op=True)
+            all_reduce_async()
+
+    def all_reduce_async():
+        """Sum the gradient buffer over the ranks, overlapped with the following kernels."""
+        if mm is not None:
+            mm["ev"].record(stream)
+            mm["stream"].wait_event(mm["ev"])
+            with torch.cuda.stream(mm["stream"]):
+                mm["hdl"].barrier(channel=0)
+                _lib.check(lib.simulst_multimem_allreduce_f32(mm["ptr"], GRAD_BUF_ELEMS, rank, world, mm["ctas"],
+                                                              mm["stream"].cuda_stream),
+                           "simulst_multimem_allreduce_f32")
+                mm["hdl"].barrier(channel=1)
+            pending[0] = mm
+            return
+        if pending[0] is not None:
+            pending[0].wait()
+        pending[0] = dist.all_reduce(grad_buf, async_op=True)
+
+    def all_reduce_join():
+        if pending[0] is None:
+            return
+        if mm is not None:
+            stream.wait_stream(mm["stream"])
+        else:
+            pending[0].wait()
+        pending[0] = None
 
     def barrier():
         if world > 1:
@@ -327,9 +382,7 @@ def run_ours(args):
     t_begin.record(stream)
     for k in range(args.steps):
         step(ev[k])
-    if pending[0] is not None:
-        pending[0].wait()
-        pending[0] = None
+    all_reduce_join()
     t_end.record(stream)
     barrier()
     launches = simulst_b200.launch_count()
@@ -353,9 +406,7 @@ def run_ours(args):
     def e2e_step():
         pipe.step(p_host, e_host, ga, gb, gp_host, ge_host)
         if world > 1:
-            if pending[0] is not None:
-                pending[0].wait()
-            pending[0] = dist.all_reduce(grad_buf, async_op=True)
+            all_reduce_async()
 
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
@@ -365,9 +416,7 @@ def run_ours(args):
     t_begin.record(stream)
     for _ in range(e2e_steps):
         e2e_step()
-    if pending[0] is not None:
-        pending[0].wait()
-        pending[0] = None
+    all_reduce_join()
     t_end.record(stream)
     barrier()
     e2e_launches = simulst_b200.launch_count()
@@ -509,6 +558,14 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if world > 1:
+            line["all_reduce"] = ({"impl": "simulst_multimem_allreduce_f32 (NVSwitch multicast ld_reduce + st), "
+                                           f"{mm['ctas']} CTAs, symmetric buffer {GRAD_BUF_ELEMS * 4 / 1e6:.1f} MB, "
+                                           "overlapped with the next step"}
+                                  if mm is not None else
+                                  {"impl": "NCCL all_reduce (async), NCCL_MAX_NCHANNELS=" +
+                                           os.environ.get("NCCL_MAX_NCHANNELS", "default"),
+                                   "multimem_unavailable": mm_note})
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         line.update(extras)

@@ -238,6 +238,19 @@ int simulst_mma_train_bwd_pooled(const void* p_pooled, int p_dtype, int ratio,
                                  void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Gradient all-reduce of the training step over NVSwitch multicast (the path shards
+ * by utterance with no data-path collective; the step it sits in sums parameter gradients once).
+ * In-place SUM over `world` ranks of a symmetric fp32 buffer that has a multicast mapping: rank r
+ * pulls the switch-reduced sum of its 1/world slice (multimem.ld_reduce) and pushes it to every
+ * rank (multimem.st), from `ctas` CTAs of 512 threads -- a few CTAs instead of the SM footprint of
+ * a ring all-reduce that overlaps compute.  The caller owns the symmetric allocation and the
+ * cross-rank barriers before and after (torch.distributed._symmetric_memory: empty / rendezvous /
+ * handle.multicast_ptr / handle.barrier); there is no reference counterpart (fairseq's DDP).
+ *   multicast_ptr  multicast address of the buffer (16-byte aligned), numel a multiple of 4 */
+int simulst_multimem_allreduce_f32(void* multicast_ptr, long long numel, int rank, int world,
+                                   int ctas, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Latency loss next to the expected-delay epilogue.
  * DifferentiableAverageLagging as called by MMACriterion.compute_latency_loss
  * (codebase/criterion/mma_criterion.py:172-177) and CIFCriterion.compute_latency_loss

@@ -69,6 +69,7 @@ SIGNATURES = {
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                              c_int, c_int, c_int, c_float, c_int, c_uint, c_void_p]),
+    "simulst_multimem_allreduce_f32": (c_int, [c_void_p, c_longlong, c_int, c_int, c_int, c_void_p]),
     "simulst_dal_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "simulst_dal_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                 c_void_p]),
