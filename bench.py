@@ -554,7 +554,11 @@ def run_ours(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                     "steps": e2e_steps, "api": "simulst_b200.host_pipeline.MMAHostPipeline.step",
                     "row_chunks": len(pipe.bounds), "compute_streams": len(pipe.s_comp),
-                    "gpu_launches": int(e2e_launches)},
+                    "gpu_launches": int(e2e_launches),
+                    "host_link_gbs_all_ranks": (h2d + d2h) * world / (e2e_ms * 1e-3) / 1e9,
+                    "note": "PCIe / host-memory bound: 268 MB up + 268 MB down per rank and step; one rank alone "
+                            "moves ~87 GB/s (both directions together), all ranks of one box share the host's "
+                            "root complexes and memory (DESIGN.md 6)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -743,7 +747,8 @@ def side_benchmarks(lib, dev):
         out["incremental_step"]["cpu_baseline"] = step_cpu_baseline(p.cpu(), se.cpu())
     except Exception as exc:  # pragma: no cover
         out["incremental_step"] = {"error": repr(exc)}
-    for name, fn in (("config1_forward", bench_config1), ("pooled_p_choose", bench_pooled)):
+    for name, fn in (("config1_forward", bench_config1), ("pooled_p_choose", bench_pooled),
+                     ("ssnt_loss", bench_ssnt), ("ctc_best_alignment", bench_ctc), ("latency_dal", bench_dal)):
         try:
             out[name] = fn(lib, dev)
         except Exception as exc:  # pragma: no cover
@@ -973,6 +978,162 @@ def bench_pooled(lib, dev):
                      "roofline_frac": elems * (bytes_f + bytes_b) / (us_p * 1e-6) / 1e9 / peak}
     out["value"] = out["full_outputs"]["value"]
     return out
+
+
+def _cpu_best(fn, reps=2):
+    """Best wall time of `fn` over `reps` runs after one warm-up, all host cores."""
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    fn()
+    best = float("inf")
+    for _ in range(reps):
+        c0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - c0)
+    return best, torch.get_num_threads()
+
+
+def bench_ssnt(lib, dev):
+    """ssnt_loss forward + backward (criterion/ssnt_loss/ssnt_loss.py:45-151) next to
+    the reference function on this box's cores, same inputs."""
+    import torch
+    from simulst_b200.criterion.ssnt_loss import ssnt_loss
+    n, t, s, v = 16, 48, 192, 256
+    g = torch.Generator().manual_seed(6100)
+    logits = torch.randn(n, t, s, v, generator=g)
+    emit = torch.randn(n, t, s, generator=g) - 1.0
+    targets = torch.randint(0, v, (n, t), generator=g)
+    src_len = torch.randint(s // 2, s + 1, (n,), generator=g)
+    tgt_len = torch.randint(t // 2, t + 1, (n,), generator=g)
+    src_len[0], tgt_len[0] = s, t
+    lp_d = logits.to(dev).log_softmax(-1).requires_grad_()
+    em_d = emit.to(dev).requires_grad_()
+    args_d = (targets.to(dev), src_len.to(dev), tgt_len.to(dev))
+
+    def step():
+        lp_d.grad = None
+        em_d.grad = None
+        loss, _, _ = ssnt_loss(lp_d, *args_d, emit_logits=em_d, reduction="sum")
+        loss.backward()
+        return loss
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    us = _events_us(step, 10)
+    out = {"metric": "ssnt_loss_fwd_bwd_us", "value": us, "unit": "us",
+           "config": f"N={n} T={t} S={s} V={v} fp32, ragged lengths, emit logits, reduction sum; through the Python mirror "
+                     "(log_probs gradient [N,T,S,V] included)",
+           "lattice_cells_per_s": n * t * s / (us * 1e-6)}
+    try:
+        from oracle import ref_loader
+        if ref_loader.available():
+            ref = ref_loader.load_ssnt().ssnt_loss
+            lp_c = logits.log_softmax(-1).requires_grad_()
+            em_c = emit.clone().requires_grad_()
+
+            def cpu_step():
+                lp_c.grad = None
+                em_c.grad = None
+                loss_c, _, _ = ref(lp_c, targets, src_len, tgt_len, emit_logits=em_c, reduction="sum")
+                loss_c.backward()
+                return loss_c
+            sec, cores = _cpu_best(cpu_step)
+            l_ref = float(cpu_step())
+            l_got = float(step())
+            if abs(l_got - l_ref) > 1e-4 * abs(l_ref):
+                raise SystemExit(f"ssnt bench parity check failed: {l_got} vs {l_ref}")
+            out["cpu_baseline"] = {"value": sec * 1e6, "unit": "us", "cores": cores, "kind": "reference",
+                                   "sample": "full config, best of 2 after 1 warm-up",
+                                   "loss_rel_diff": abs(l_got - l_ref) / abs(l_ref)}
+    except SystemExit:
+        raise
+    except Exception as exc:  # pragma: no cover
+        out["cpu_baseline"] = {"error": repr(exc)}
+    return out
+
+
+def bench_ctc(lib, dev):
+    """CTC best alignment (criterion/best_alignment: the reference's one native
+    kernel + its S-iteration Python back-trace) at the CIF criterion's shape: B=64 utterances,
+    375 encoder frames, 60-token targets, V=1024.  Baselines: the reference's Python wrapper over
+    its own JIT-built CUDA kernel on this GPU (when it builds here), checked equal."""
+    import torch
+    from simulst_b200.criterion.best_alignment import best_alignment
+    b, s, t, v = 64, 375, 60, 1024
+    g = torch.Generator().manual_seed(6200)
+    lp = torch.randn(s, b, v, generator=g).log_softmax(-1).to(dev)
+    targets = torch.randint(1, v, (b, t), generator=g).to(dev)
+    in_len = torch.randint(s // 2, s + 1, (b,), generator=g).to(dev)
+    tg_len = torch.randint(t // 2, t + 1, (b,), generator=g).to(dev)
+    in_len[0], tg_len[0] = s, t
+    for _ in range(3):
+        states = best_alignment(lp, targets, in_len, tg_len)
+    torch.cuda.synchronize()
+    us = _events_us(lambda: best_alignment(lp, targets, in_len, tg_len), 10)
+    out = {"metric": "ctc_best_alignment_us", "value": us, "unit": "us",
+           "config": f"B={b} S={s} T={t} V={v} fp32 log-probs, ragged lengths; one launch incl. the back-trace",
+           "frames_per_s": b * s / (us * 1e-6)}
+    try:
+        from oracle import ref_loader
+        if ref_loader.available():
+            ext = ref_loader.load_best_alignment_extension()
+            ref_call = ref_loader.load_best_alignment_python()
+            ref_states = ref_call(ext, lp, targets, in_len, tg_len)
+            torch.cuda.synchronize()
+            ref_us = _events_us(lambda: ref_call(ext, lp, targets, in_len, tg_len), 3)
+            out["reference_gpu"] = {"value": ref_us, "unit": "us", "kind": "reference",
+                                    "what": "criterion/best_alignment/__init__.py over the reference's own CUDA kernel "
+                                            "(JIT-built here), same GPU",
+                                    "states_equal": bool(torch.equal(states, ref_states))}
+            if not out["reference_gpu"]["states_equal"]:
+                raise SystemExit("ctc bench parity check failed: alignment differs from the reference's")
+    except SystemExit:
+        raise
+    except Exception as exc:  # pragma: no cover
+        out["reference_gpu"] = {"error": repr(exc)[:300]}
+    return out
+
+
+def bench_dal(lib, dev):
+    """DifferentiableAverageLagging forward + backward on the [N,T] expected delays
+    (criterion/mma_criterion.py:172-177), against SimulEval's formulation (restated in
+    oracle/latency.py -- the function is not vendored by the reference) on this box's cores."""
+    import torch
+    from simulst_b200 import ops
+    n, t = 64 * 6 * 8, 128          # batch x layers x heads rows, as compute_latency_loss flattens them
+    g = torch.Generator().manual_seed(6300)
+    delays = (torch.rand(n, t, generator=g) * 1000.0).cumsum(1) / 64.0
+    src = torch.randint(512, 1025, (n,), generator=g)
+    mask = torch.arange(t)[None, :] >= torch.randint(t // 2, t + 1, (n, 1), generator=g)
+    d_d = delays.to(dev).requires_grad_()
+    src_d, mask_d = src.to(dev), mask.to(dev)
+
+    def step():
+        d_d.grad = None
+        out = ops.differentiable_average_lagging(d_d, src_d, None, mask_d)
+        out.sum().backward()
+        return out
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    us = _events_us(step, 10)
+    res = {"metric": "dal_fwd_bwd_us", "value": us, "unit": "us", "config": f"{n} rows x tgt {t}, target padding mask"}
+    try:
+        from oracle import latency as olat
+        d_c = delays.clone().requires_grad_()
+
+        def cpu_step():
+            d_c.grad = None
+            o = olat.differentiable_average_lagging(d_c, src, None, mask)
+            o.sum().backward()
+            return o
+        sec, cores = _cpu_best(cpu_step)
+        diff = float((step().detach().cpu() - cpu_step().detach()).abs().max())
+        res["cpu_baseline"] = {"value": sec * 1e6, "unit": "us", "cores": cores, "kind": "port",
+                               "sample": "full config, best of 2 after 1 warm-up", "max_abs_diff": diff}
+    except Exception as exc:  # pragma: no cover
+        res["cpu_baseline"] = {"error": repr(exc)[:300]}
+    return res
 
 
 def main():
