@@ -5,8 +5,10 @@
 The reference computes p_choose on the POOLED keys (``[N,T,ceil(S/ratio)]``, :107-137), blows it
 up to ``[N,T,S]`` with a transposed convolution (``insert_zeros``, :85-95), patches the last
 column (:139-159) and then runs the dense alignment functions over a tensor that is (ratio-1)/ratio
-zeros.  Here the pooled tensor goes straight to ``simulst_mma_train_fwd_pooled``: the kernels form
-the zero-upsampled row in registers, and the backward returns the gradient of the pooled tensor.
+zeros.  Here the pooled tensor goes straight to ``simulst_mma_train_fwd_pooled``: alpha is zero off
+the pooled grid, so the recurrence runs on ``[N,T,ceil(S/ratio)]`` only, streaming row kernels produce
+the soft attention and the dense outputs (csrc/mma_sparse.cu), and the backward returns the gradient of
+the pooled tensor.
 
 ``B200FixedStrideMixin`` goes in front of a class produced by the reference's
 ``fixed_pooling_monotonic_attention`` decorator (or apply ``patch_fixed_pre_decision(cls)``); it
@@ -66,7 +68,7 @@ class B200FixedStrideMixin(B200MonotonicAttentionMixin):
         key_padding_mask: Optional[Tensor] = None,
     ):
         """reference monotonic_multihead_attention.py:301-352 with p_choose() of
-        fixed_pre_decision.py:96-170 folded in: ONE launch from the pooled p_choose."""
+        fixed_pre_decision.py:96-170 folded in: the pooled p_choose goes to the kernels as it is."""
         assert query is not None
         assert key is not None
         src_len = key.size(0)
