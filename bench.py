@@ -1038,8 +1038,8 @@ def bench_ssnt(lib, dev):
                 loss_c.backward()
                 return loss_c
             sec, cores = _cpu_best(cpu_step)
-            l_ref = float(cpu_step())
-            l_got = float(step())
+            l_ref = float(cpu_step().detach())
+            l_got = float(step().detach())
             if abs(l_got - l_ref) > 1e-4 * abs(l_ref):
                 raise SystemExit(f"ssnt bench parity check failed: {l_got} vs {l_ref}")
             out["cpu_baseline"] = {"value": sec * 1e6, "unit": "us", "cores": cores, "kind": "reference",

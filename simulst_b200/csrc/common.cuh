@@ -242,6 +242,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
                  "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     asm volatile(
         "{\n\t"
@@ -254,6 +257,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         "}" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+}
+// mbar_wait for warps with slack (producers / consumers around a latency-critical warp): back off
+// between polls so the polling does not take issue slots from the warp everybody waits for
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!done) __nanosleep(40);
+    } while (!done);
 }
 // 1-D bulk async copy global -> shared, completion signalled on an mbarrier (TMA engine;
 // SASS: UBLKCP).  dst/src 16-byte aligned, bytes a multiple of 16.

@@ -31,6 +31,7 @@
 // right-padding mask promised by SIMULST_MMA_RIGHT_PADDING (verified per row, like the dense
 // MASKED kernels: a violation sets SIMULST_ST_NOT_RIGHT_PADDED and poisons the row with NaN).
 #include <algorithm>
+#include <cstdlib>
 
 #include "mma_scan.cuh"
 #include "mma_sparse.h"
@@ -38,6 +39,9 @@
 namespace simulst {
 
 namespace {
+
+// development knob (SIMULST_SPARSE_VARIANT): 0 warp-specialised K1/K4 (default), 1 single-warp pipelined, 2 generic
+static const int g_sparse_variant = [] { const char* e = getenv("SIMULST_SPARSE_VARIANT"); return e ? atoi(e) : 0; }();
 
 constexpr float kLog2eS = 1.4426950408889634f;
 // K2 / K3: rows staged ahead by TMA (ring depth; long rows get a shallower ring to fit 227 KB)
@@ -857,8 +861,11 @@ sparse_row_fwd_last_kernel(const SparseParams prm, int rows_per_cta) {
     }
 }
 
+#ifndef SIMULST_K3_THREADS_PER_SM
+#define SIMULST_K3_THREADS_PER_SM 1024
+#endif
 template <int THREADS, typename T>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 1024 / THREADS : 1))
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? SIMULST_K3_THREADS_PER_SM / THREADS : 1))
 sparse_row_bwd_last_kernel(const SparseParams prm, int rows_per_cta) {
     constexpr int VPT = 8, NW = THREADS / 32, CAP = THREADS * VPT;
     constexpr int kRing = ring_bwd(CAP);
@@ -1709,6 +1716,465 @@ __global__ void __launch_bounds__(32) sparse_alpha_bwd_w1_kernel(const SparsePar
     }
 }
 
+
+// =============================================================================================
+// K1 / K4, warp-specialised (rows whose grid fits one warp: Sp <= 32 * EPT).  A single warp that
+// does everything issues ~240 (forward) / ~500 (backward) instructions per step in order, at one
+// instruction per ~4.4 cycles: the recurrence waits behind work that does not depend on it.  Here
+// the step is split by DEPENDENCE, one role per warp group, connected by shared-memory rings with
+// full / empty mbarriers:
+//   producers  (NP warps, step i -> warp i % NP)   everything that does not depend on the recurrence:
+//              loads, cumprod scan, clamp, 1/c, P (backward: also u, s, clamp masks, upstream gradient)
+//   chain      (warp 0)   the recurrence itself: one multiply, one scan, one clamp per step
+//   consumers  (NC warps) everything downstream: row sums, mass preservation, delays, stores
+//              (backward: the exclusive suffix scan and the gradient of the pooled p_choose)
+// The chain warp's step is ~45 instructions around one shuffle scan.
+constexpr int kWsDepth = 8;
+
+template <int EPT, int NP, int NC, typename T>
+__global__ void __launch_bounds__((1 + NP + NC) * 32) sparse_alpha_fwd_ws_kernel(const SparseParams prm) {
+    constexpr int CAPP = 32 * EPT, THREADS = (1 + NP + NC) * 32;
+    __shared__ __align__(16) float ringP[kWsDepth][CAPP], ringRc[kWsDepth][CAPP], ringA[kWsDepth][CAPP];
+    __shared__ __align__(8) uint64_t fullA[kWsDepth], fullC[kWsDepth], emptyC[kWsDepth];
+    __shared__ int sh_int[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.x;
+    const int S = prm.S, Sp = prm.Sp, r = prm.r, T_len = prm.T;
+    const float eps = prm.eps;
+    const bool mp = (prm.flags & SIMULST_MMA_MASS_PRESERVATION) != 0u;
+    const bool replace = prm.mask == nullptr;
+
+    const RowGeom geo = row_geometry<THREADS>(prm, n, sh_int);
+    if (tid == 0) { prm.lens[n] = geo.L; prm.xcol[n] = geo.xcol; }
+    float* asp = prm.a_sp + (size_t)n * T_len * Sp;
+    float* ax = prm.a_x + (size_t)n * T_len;
+    float4* info = prm.mp_info + (size_t)n * T_len;
+    if (geo.L < 0) {
+        if (tid == 0 && prm.status != nullptr) atomicOr(prm.status, SIMULST_ST_NOT_RIGHT_PADDED);
+        const float qnan = __int_as_float(0x7fc00000);
+        for (size_t q = tid; q < (size_t)T_len * Sp; q += THREADS) asp[q] = qnan;
+        for (int q = tid; q < T_len; q += THREADS) { ax[q] = qnan; info[q] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        return;
+    }
+    if (tid == 0) {
+        for (int s2 = 0; s2 < kWsDepth; ++s2) { mbar_init(&fullA[s2], 1); mbar_init(&fullC[s2], 1); mbar_init(&emptyC[s2], 1); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int L = geo.L;
+    const int m0 = lane * EPT;
+    bool valid[EPT], live[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        valid[k] = m0 + k < Sp;
+        live[k] = valid[k] && grid_col(m0 + k, Sp, S, r) < L;
+    }
+
+    if (warp == 0) {
+        // ------------------------------------------------ chain: u = alpha_{i-1} / c ; s = prefix(u) ; alpha_i = clamp(P s)
+        float a_prev[EPT];
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) a_prev[k] = (S == 1 && m0 + k == 0) ? 1.0f : 0.0f;
+        for (int i = 0; i < T_len; ++i) {
+            const int slot = i % kWsDepth;
+            mbar_wait(&fullA[slot], (unsigned)((i / kWsDepth) & 1));
+            float P[EPT], rc[EPT], u[EPT], ut = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < EPT / 4; ++c4) {
+                const float4 pv = *reinterpret_cast<const float4*>(&ringP[slot][m0 + 4 * c4]);
+                const float4 rv = *reinterpret_cast<const float4*>(&ringRc[slot][m0 + 4 * c4]);
+                P[4 * c4] = pv.x; P[4 * c4 + 1] = pv.y; P[4 * c4 + 2] = pv.z; P[4 * c4 + 3] = pv.w;
+                rc[4 * c4] = rv.x; rc[4 * c4 + 1] = rv.y; rc[4 * c4 + 2] = rv.z; rc[4 * c4 + 3] = rv.w;
+            }
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                ut += a_prev[k] * rc[k];
+                u[k] = ut;
+            }
+            const float inc = wscan_prefix_add(ut);
+            const float s_off = wprev(inc, 0.f) + ((i == 0 && S != 1) ? 1.0f : 0.0f);
+            float a[EPT];
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                a[k] = fminf(fmaxf(P[k] * (s_off + u[k]), 0.0f), 1.0f);
+                a_prev[k] = a[k];
+            }
+#pragma unroll
+            for (int c4 = 0; c4 < EPT / 4; ++c4)
+                *reinterpret_cast<float4*>(&ringA[slot][m0 + 4 * c4]) = make_float4(a[4 * c4], a[4 * c4 + 1], a[4 * c4 + 2], a[4 * c4 + 3]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&fullC[slot]);
+        }
+    } else if (warp <= NP) {
+        // ------------------------------------------------ producers: P = p * cp, 1 / clamp(cp)
+        const int w = warp - 1;
+        float W[EPT];
+        const double log1e = log((double)(1.0f + eps));
+#pragma unroll
+        for (int k = 0; k < EPT; ++k)
+            W[k] = valid[k] ? (float)exp((double)(1 + grid_col(m0 + k, Sp, S, r) - (m0 + k)) * log1e) : 1.0f;
+        const T* gpp = reinterpret_cast<const T*>(prm.pp) + (size_t)n * T_len * Sp;
+        unsigned umax = 0u;
+        unsigned raw[EPT];
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) raw[k] = (valid[k] && w < T_len) ? ldg_raw<T>(gpp + (size_t)w * Sp + m0 + k) : 0u;
+        for (int i = w; i < T_len; i += NP) {
+            float p[EPT], xe[EPT], xt = 1.0f;
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                umax = max(umax, sizeof(T) == 4 ? raw[k] : raw[k] << 16);
+                const float v = raw_to_f32<T>(raw[k]);
+                p[k] = live[k] ? v : 0.f;
+                xe[k] = xt;
+                xt *= (1.0f - p[k]) + eps;
+            }
+            if (i + NP < T_len) {
+#pragma unroll
+                for (int k = 0; k < EPT; ++k) raw[k] = valid[k] ? ldg_raw<T>(gpp + (size_t)(i + NP) * Sp + m0 + k) : 0u;
+            }
+            const float xoff = wprev(wscan_prefix_mul(xt), 1.0f);
+            float P[EPT], rc[EPT];
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                const float cp = W[k] * (xoff * xe[k]);
+                P[k] = p[k] * cp;
+                rc[k] = fast_rcp(fminf(fmaxf(cp, eps), 1.0f));
+            }
+            const int slot = i % kWsDepth;
+            mbar_wait_relaxed(&emptyC[slot], (unsigned)(((i / kWsDepth) & 1) ^ 1));
+#pragma unroll
+            for (int c4 = 0; c4 < EPT / 4; ++c4) {
+                *reinterpret_cast<float4*>(&ringP[slot][m0 + 4 * c4]) = make_float4(P[4 * c4], P[4 * c4 + 1], P[4 * c4 + 2], P[4 * c4 + 3]);
+                *reinterpret_cast<float4*>(&ringRc[slot][m0 + 4 * c4]) = make_float4(rc[4 * c4], rc[4 * c4 + 1], rc[4 * c4 + 2], rc[4 * c4 + 3]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&fullA[slot]);
+        }
+        // prob_check / safe_cumprod's sign check: bit patterns above 1.0f are NaN, > 1 or negative; the
+        // exact classification only runs when the cheap test trips
+        if (prm.status != nullptr && __any_sync(kFull, umax > 0x3f800000u)) {
+            unsigned bits = 0u;
+            for (int i = w; i < T_len; i += NP)
+                for (int m = lane; m < Sp; m += 32) {
+                    const float v = to_f32<T>(gpp[(size_t)i * Sp + m]);
+                    bits |= prob_bits(v) | ((((1.0f - v) + eps) < 0.f) ? SIMULST_ST_NEGPROD : 0u);
+                }
+            bits = __reduce_or_sync(kFull, bits);
+            if (lane == 0 && bits) atomicOr(prm.status, bits);
+        }
+    } else {
+        // ------------------------------------------------ consumers: row sums, mass preservation, delays, stores
+        const int w = warp - 1 - NP;
+        const bool has_res = mp && (geo.mp_m >= 0 || geo.xcol >= 0);
+        const int k_mp = (mp && geo.mp_m >= m0 && geo.mp_m < m0 + EPT) ? geo.mp_m - m0 : -1;
+        float wcolm[EPT], summ[EPT];
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const bool excl = replace && k == k_mp;         // REPLACE: the residual excludes the column itself
+            summ[k] = excl ? 0.f : 1.0f;
+            wcolm[k] = excl ? 0.f : (valid[k] ? (float)(grid_col(m0 + k, Sp, S, r) + 1) : 0.f);
+        }
+        const float w_mp = geo.mp_m >= 0 ? (float)(grid_col(geo.mp_m, Sp, S, r) + 1) : (float)(geo.xcol + 1);
+        const bool vec_store = (Sp % EPT) == 0;
+        const bool info_lane = geo.mp_m >= 0 ? (k_mp >= 0) : (lane == 0);      // the lane holding the raw column value
+        for (int i = w; i < T_len; i += NC) {
+            const int slot = i % kWsDepth;
+            mbar_wait_relaxed(&fullC[slot], (unsigned)((i / kWsDepth) & 1));
+            float a[EPT];
+#pragma unroll
+            for (int c4 = 0; c4 < EPT / 4; ++c4) {
+                const float4 av = *reinterpret_cast<const float4*>(&ringA[slot][m0 + 4 * c4]);
+                a[4 * c4] = av.x; a[4 * c4 + 1] = av.y; a[4 * c4 + 2] = av.z; a[4 * c4 + 3] = av.w;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&emptyC[slot]);
+            float pa = 0.f, pw = 0.f;
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                pa += a[k] * summ[k];
+                pw += a[k] * wcolm[k];
+            }
+            pa = warp_sum(pa);
+            pw = warp_sum(pw);
+            const float res = has_res ? 1.0f - fminf(fmaxf(pa, 0.0f), 1.0f) : 0.f;
+            float raw_v = 0.f;
+            if (k_mp >= 0) {
+#pragma unroll
+                for (int k = 0; k < EPT; ++k)
+                    if (k == k_mp) { raw_v = a[k]; a[k] = replace ? res : a[k] + res; }
+            }
+            if (info_lane) {
+                info[i] = make_float4(pa, raw_v, 0.f, 0.f);
+                if (mp && prm.side != nullptr) {
+                    prm.side[((size_t)n * T_len + i) * 2] = raw_v;
+                    prm.side[((size_t)n * T_len + i) * 2 + 1] = pa;
+                }
+            }
+            if (lane == 0) {
+                ax[i] = (mp && geo.xcol >= 0) ? res : 0.f;
+                if (prm.delays != nullptr) prm.delays[(size_t)n * T_len + i] = has_res ? pw + w_mp * res : pw;
+            }
+            float* arow = asp + (size_t)i * Sp + m0;
+            if (vec_store) {
+                if (valid[0]) {
+#pragma unroll
+                    for (int c4 = 0; c4 < EPT / 4; ++c4)
+                        *reinterpret_cast<float4*>(arow + 4 * c4) = make_float4(a[4 * c4], a[4 * c4 + 1], a[4 * c4 + 2], a[4 * c4 + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < EPT; ++k)
+                    if (valid[k]) arow[k] = a[k];
+            }
+        }
+    }
+}
+
+template <int EPT, int NP, int NC, typename T>
+__global__ void __launch_bounds__((1 + NP + NC) * 32) sparse_alpha_bwd_ws_kernel(const SparseParams prm) {
+    constexpr int CAPP = 32 * EPT, THREADS = (1 + NP + NC) * 32;
+    // per slot: producer -> chain {ga, mz*P, 1/c}; chain -> consumer {g, carry}; producer -> consumer {mz*s, p, u*pass, cp, 1/x}
+    extern __shared__ __align__(128) unsigned char smem_ws[];
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(smem_ws);
+    uint64_t* fullC = fullA + kWsDepth;
+    uint64_t* emptyC = fullC + kWsDepth;
+    float* ring = reinterpret_cast<float*>(smem_ws + 256);
+    auto slot_arr = [&](int slot, int which) { return ring + ((size_t)slot * 10 + which) * CAPP; };
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.x;
+    const int S = prm.S, Sp = prm.Sp, r = prm.r, T_len = prm.T;
+    const float eps = prm.eps;
+    const bool mp = (prm.flags & SIMULST_MMA_MASS_PRESERVATION) != 0u;
+    const bool replace = prm.mask == nullptr;
+    const int m0 = lane * EPT;
+    T* gout = reinterpret_cast<T*>(prm.g_pp) + (size_t)n * T_len * Sp;
+
+    const int L = prm.lens[n];
+    const int xcol = prm.xcol[n];
+    if (L < 0) {
+        for (size_t q = tid; q < (size_t)T_len * Sp; q += THREADS) gout[q] = from_f32<T>(0.f);
+        return;
+    }
+    if (tid == 0) {
+        for (int s2 = 0; s2 < kWsDepth; ++s2) { mbar_init(&fullA[s2], 1); mbar_init(&fullC[s2], 1); mbar_init(&emptyC[s2], 1); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    bool valid[EPT], live[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        valid[k] = m0 + k < Sp;
+        live[k] = valid[k] && grid_col(m0 + k, Sp, S, r) < L;
+    }
+    auto ld4 = [&](const float* src, float (&v)[EPT]) {
+#pragma unroll
+        for (int c4 = 0; c4 < EPT / 4; ++c4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(src + m0 + 4 * c4);
+            v[4 * c4] = t4.x; v[4 * c4 + 1] = t4.y; v[4 * c4 + 2] = t4.z; v[4 * c4 + 3] = t4.w;
+        }
+    };
+    auto st4 = [&](float* dst, const float (&v)[EPT]) {
+#pragma unroll
+        for (int c4 = 0; c4 < EPT / 4; ++c4)
+            *reinterpret_cast<float4*>(dst + m0 + 4 * c4) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+    };
+    // steps are walked T-1 .. 0; q = T-1-i is the processing index that selects ring slot and phase
+
+    if (warp == 0) {
+        // ------------------------------------------------ chain: g = ga + carry ; gu = suffix(g * mz * P) ; carry = gu / c
+        float carry[EPT];
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) carry[k] = 0.f;
+        for (int q = 0; q < T_len; ++q) {
+            const int slot = q % kWsDepth;
+            mbar_wait(&fullA[slot], (unsigned)((q / kWsDepth) & 1));
+            float ga[EPT], mzP[EPT], rc[EPT], g[EPT], gsl[EPT], gst = 0.f;
+            ld4(slot_arr(slot, 0), ga);
+            ld4(slot_arr(slot, 1), mzP);
+            ld4(slot_arr(slot, 2), rc);
+#pragma unroll
+            for (int k = EPT - 1; k >= 0; --k) {
+                g[k] = ga[k] + carry[k];
+                gst += g[k] * mzP[k];
+                gsl[k] = gst;
+            }
+            const float off = wnext(wscan_suffix_add(gst), 0.f);
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) carry[k] = (off + gsl[k]) * rc[k];
+            st4(slot_arr(slot, 3), g);
+            st4(slot_arr(slot, 4), carry);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&fullC[slot]);
+        }
+    } else if (warp <= NP) {
+        // ------------------------------------------------ producers: recompute the forward quantities of a step
+        const int w = warp - 1;
+        int mp_m = -1;
+        if (mp) {
+            if (replace) mp_m = Sp - 1;
+            else if (L > 0 && xcol < 0) mp_m = grid_idx(L - 1, Sp, S, r);
+        }
+        const bool has_mp = mp && (mp_m >= 0 || xcol >= 0);
+        const int k_mp = (mp_m >= m0 && mp_m < m0 + EPT) ? mp_m - m0 : -1;
+        const int mp_lane = mp_m >= 0 ? mp_m / EPT : 0;
+        float W[EPT];
+        const double log1e = log((double)(1.0f + eps));
+#pragma unroll
+        for (int k = 0; k < EPT; ++k)
+            W[k] = valid[k] ? (float)exp((double)(1 + grid_col(m0 + k, Sp, S, r) - (m0 + k)) * log1e) : 1.0f;
+        const T* gpp = reinterpret_cast<const T*>(prm.pp) + (size_t)n * T_len * Sp;
+        const float* asp = prm.a_sp + (size_t)n * T_len * Sp;
+        const float* gsp = prm.g_sp + (size_t)n * T_len * Sp;
+        const float4* info = prm.mp_info + (size_t)n * T_len;
+        const float4* gx4 = prm.g_x4 + (size_t)n * T_len;
+        // operands of this warp's next step, fetched one own-step ahead
+        unsigned raw_p[EPT];
+        float am1_n[EPT], G_n[EPT], ssum_n = 0.f, rawprev_n = 0.f, gx_n = 0.f;
+        auto fetch = [&](int i) {
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                raw_p[k] = valid[k] ? ldg_raw<T>(gpp + (size_t)i * Sp + m0 + k) : 0u;
+                G_n[k] = valid[k] ? __ldg(gsp + (size_t)i * Sp + m0 + k) : 0.f;
+                am1_n[k] = (valid[k] && i > 0) ? __ldg(asp + (size_t)(i - 1) * Sp + m0 + k) : 0.f;
+            }
+            if (has_mp) {
+                ssum_n = __ldg(&info[i].x);
+                if (i > 0 && mp_m >= 0) rawprev_n = __ldg(&info[i - 1].y);
+                if (xcol >= 0) gx_n = __ldg(&gx4[i].x);
+            }
+        };
+        if (w < T_len) fetch(T_len - 1 - w);
+        for (int q = w; q < T_len; q += NP) {
+            const int i = T_len - 1 - q;
+            float p[EPT], G[EPT], am1[EPT];
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                p[k] = live[k] ? raw_to_f32<T>(raw_p[k]) : 0.f;
+                G[k] = live[k] ? G_n[k] : 0.f;
+                am1[k] = am1_n[k];
+            }
+            const float ssum = ssum_n, rawprev = rawprev_n, gx_i = gx_n;
+            if (q + NP < T_len) fetch(i - NP);
+            if (i == 0) {
+#pragma unroll
+                for (int k = 0; k < EPT; ++k) am1[k] = (S == 1 && m0 + k == 0) ? 1.0f : 0.0f;
+            } else if (k_mp >= 0) {                       // undo mass preservation on the stored row
+#pragma unroll
+                for (int k = 0; k < EPT; ++k) am1[k] = (k == k_mp) ? rawprev : am1[k];
+            }
+            float gmp = 0.f;
+            if (has_mp) {
+                float cand = gx_i;
+                if (xcol < 0) {
+                    float own = 0.f;
+#pragma unroll
+                    for (int k = 0; k < EPT; ++k) own = (k == k_mp) ? G[k] : own;
+                    cand = __shfl_sync(kFull, own, mp_lane);
+                }
+                gmp = (ssum >= 0.0f && ssum <= 1.0f) ? cand : 0.f;
+            }
+            float x[EPT], xe[EPT], xt = 1.0f;
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                x[k] = (1.0f - p[k]) + eps;
+                xe[k] = xt;
+                xt *= x[k];
+            }
+            const float xoff = wprev(wscan_prefix_mul(xt), 1.0f);
+            float cp[EPT], rc[EPT], pass[EPT], P[EPT], u[EPT], sl[EPT], ut = 0.f;
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                cp[k] = W[k] * (xoff * xe[k]);
+                const float cc = fminf(fmaxf(cp[k], eps), 1.0f);
+                rc[k] = fast_rcp(cc);
+                pass[k] = (cc == cp[k]) ? 1.0f : 0.0f;
+                P[k] = p[k] * cp[k];
+                u[k] = am1[k] * rc[k];
+                ut += u[k];
+                sl[k] = ut;
+            }
+            const float s_off = wprev(wscan_prefix_add(ut), 0.f) + ((i == 0 && S != 1) ? 1.0f : 0.0f);
+            float ga[EPT], mzP[EPT], ms[EPT], up[EPT], rx[EPT];
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                const float s = s_off + sl[k];
+                const float z = P[k] * s;
+                const float mz = (z >= 0.0f && z <= 1.0f) ? 1.0f : 0.0f;
+                float gak = G[k] - gmp;
+                if (replace && k == k_mp) gak = 0.f;
+                ga[k] = live[k] ? gak : 0.f;
+                mzP[k] = mz * P[k];
+                ms[k] = mz * s;
+                up[k] = u[k] * pass[k];
+                rx[k] = fast_rcp(x[k]);
+            }
+            const int slot = q % kWsDepth;
+            mbar_wait_relaxed(&emptyC[slot], (unsigned)(((q / kWsDepth) & 1) ^ 1));
+            st4(slot_arr(slot, 0), ga);
+            st4(slot_arr(slot, 1), mzP);
+            st4(slot_arr(slot, 2), rc);
+            st4(slot_arr(slot, 5), ms);
+            st4(slot_arr(slot, 6), p);
+            st4(slot_arr(slot, 7), up);
+            st4(slot_arr(slot, 8), cp);
+            st4(slot_arr(slot, 9), rx);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&fullA[slot]);
+        }
+    } else {
+        // ------------------------------------------------ consumers: gradient of the pooled p_choose of a step
+        const int w = warp - 1 - NP;
+        const bool vec_store = (Sp % EPT) == 0 && sizeof(T) * EPT >= 8;
+        for (int q = w; q < T_len; q += NC) {
+            const int i = T_len - 1 - q;
+            const int slot = q % kWsDepth;
+            mbar_wait_relaxed(&fullC[slot], (unsigned)((q / kWsDepth) & 1));
+            float g[EPT], carry[EPT], ms[EPT], p[EPT], up[EPT], cp[EPT], rx[EPT];
+            ld4(slot_arr(slot, 3), g);
+            ld4(slot_arr(slot, 4), carry);
+            ld4(slot_arr(slot, 5), ms);
+            ld4(slot_arr(slot, 6), p);
+            ld4(slot_arr(slot, 7), up);
+            ld4(slot_arr(slot, 8), cp);
+            ld4(slot_arr(slot, 9), rx);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&emptyC[slot]);
+            // gP = gz * s ; gcp = gP * p - carry * u * 1[eps <= cp <= 1] ; gA = gcp * cp ; gL = exclusive suffix(gA)
+            float gP[EPT], gAl[EPT], gAt = 0.f;
+#pragma unroll
+            for (int k = EPT - 1; k >= 0; --k) {
+                gP[k] = g[k] * ms[k];
+                const float gcp = gP[k] * p[k] - carry[k] * up[k];
+                gAl[k] = gAt;
+                gAt += gcp * cp[k];
+            }
+            const float off = wnext(wscan_suffix_add(gAt), 0.f);
+            T* orow = gout + (size_t)i * Sp + m0;
+            __align__(16) T ov[EPT];
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                const float o = gP[k] * cp[k] - (off + gAl[k]) * rx[k];
+                ov[k] = from_f32<T>(live[k] ? o : 0.f);
+            }
+            if (vec_store) {
+                if (valid[0]) {
+                    if constexpr (sizeof(T) * EPT == 8) {
+                        *reinterpret_cast<uint2*>(orow) = *reinterpret_cast<const uint2*>(ov);
+                    } else {
+#pragma unroll
+                        for (int c4 = 0; c4 < (int)(sizeof(T) * EPT / 16); ++c4)
+                            reinterpret_cast<uint4*>(orow)[c4] = reinterpret_cast<const uint4*>(ov)[c4];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < EPT; ++k)
+                    if (valid[k]) orow[k] = ov[k];
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ launchers
 template <typename T>
 int launch_alpha(const SparseParams& prm, bool bwd, cudaStream_t st) {
@@ -1719,9 +2185,37 @@ int launch_alpha(const SparseParams& prm, bool bwd, cudaStream_t st) {
         return check_launch();                                                                 \
     }
     const int Sp = prm.Sp;
-    // one warp per row, operands through a TMA chunk ring: rows of 16-byte multiples, 16-byte aligned blocks
-    if (Sp <= 256 && ((size_t)prm.T * Sp * sizeof(T)) % 16 == 0 && ((size_t)Sp * sizeof(T)) % 16 == 0 &&
-        (reinterpret_cast<uintptr_t>(prm.pp) % 16) == 0) {
+    // rows whose grid fits one warp: the warp-specialised kernels (2 producers + chain + 2 consumers forward,
+    // 3 + chain + 2 backward)
+    if (Sp <= 256 && g_sparse_variant == 0) {
+        static bool attr_done[2][64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const int which = Sp <= 128 ? 0 : 1;
+        if (!bwd) {
+            if (which == 0) sparse_alpha_fwd_ws_kernel<4, 2, 2, T><<<prm.N, 5 * 32, 0, st>>>(prm);
+            else sparse_alpha_fwd_ws_kernel<8, 2, 2, T><<<prm.N, 5 * 32, 0, st>>>(prm);
+            return check_launch();
+        }
+        // (2 + 2 / 3 + 2 helper warps: more of them only take issue slots from the chain warps --
+        // measured 3+3: 41 us, 4+4: 41 us forward; 4+3: 85 us, 6+4: 78 us backward)
+        const size_t smem = 256 + (size_t)kWsDepth * 10 * (which == 0 ? 128 : 256) * 4;
+        auto k4 = sparse_alpha_bwd_ws_kernel<4, 3, 2, T>;
+        auto k8 = sparse_alpha_bwd_ws_kernel<8, 3, 2, T>;
+        if (!attr_done[which][dev & 63]) {
+            if (cudaFuncSetAttribute(which == 0 ? k4 : k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+                cudaGetLastError();
+                return SIMULST_E_LAUNCH;
+            }
+            attr_done[which][dev & 63] = true;
+        }
+        if (which == 0) k4<<<prm.N, 6 * 32, smem, st>>>(prm);
+        else k8<<<prm.N, 6 * 32, smem, st>>>(prm);
+        return check_launch();
+    }
+    // single-warp pipelined kernels with TMA chunk rings (development comparison, variant 1)
+    if (Sp <= 256 && g_sparse_variant == 1 && ((size_t)prm.T * Sp * sizeof(T)) % 16 == 0 &&
+        ((size_t)Sp * sizeof(T)) % 16 == 0 && (reinterpret_cast<uintptr_t>(prm.pp) % 16) == 0) {
         if (!bwd) {
             if (Sp <= 128) sparse_alpha_fwd_w1_kernel<4, T><<<prm.N, 32, 0, st>>>(prm);
             else sparse_alpha_fwd_w1_kernel<8, T><<<prm.N, 32, 0, st>>>(prm);
