@@ -27,9 +27,9 @@ int INST_NAME(const MmaParams& prm, int mode, int threads, int vpt, cudaStream_t
             if (rc != 1) return rc;             /* 1 = row does not qualify for the dense fast path */ \
         }                                                                                 \
         switch (mode) {                                                                   \
-            case kModeHard: return launch_mma_bwd<TH, VP, InstT, kModeHard>(prm, stream); \
-            case kModeSoftIL: return launch_mma_bwd<TH, VP, InstT, kModeSoftIL>(prm, stream); \
-            case kModeSoftCk: return launch_mma_bwd<TH, VP, InstT, kModeSoftCk>(prm, stream); \
+            case kModeHard: return launch_mma_bwd<generic_threads(TH), VP, InstT, kModeHard>(prm, stream); \
+            case kModeSoftIL: return launch_mma_bwd<generic_threads(TH), VP, InstT, kModeSoftIL>(prm, stream); \
+            case kModeSoftCk: return launch_mma_bwd<generic_threads(TH), VP, InstT, kModeSoftCk>(prm, stream); \
         }                                                                                 \
     }
     SIMULST_MMA_CONFIGS(X)

@@ -28,9 +28,9 @@ int INST_NAME(const MmaParams& prm, int mode, int threads, int vpt, cudaStream_t
             }                                                                             \
         }                                                                                 \
         switch (mode) {                                                                   \
-            case kModeHard: return launch_mma_fwd<TH, VP, InstT, kModeHard>(prm, stream); \
-            case kModeSoftIL: return launch_mma_fwd<TH, VP, InstT, kModeSoftIL>(prm, stream); \
-            case kModeSoftCk: return launch_mma_fwd<TH, VP, InstT, kModeSoftCk>(prm, stream); \
+            case kModeHard: return launch_mma_fwd<generic_threads(TH), VP, InstT, kModeHard>(prm, stream); \
+            case kModeSoftIL: return launch_mma_fwd<generic_threads(TH), VP, InstT, kModeSoftIL>(prm, stream); \
+            case kModeSoftCk: return launch_mma_fwd<generic_threads(TH), VP, InstT, kModeSoftCk>(prm, stream); \
         }                                                                                 \
     }
     SIMULST_MMA_CONFIGS(X)
