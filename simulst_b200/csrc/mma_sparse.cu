@@ -2001,6 +2001,9 @@ __global__ void __launch_bounds__((1 + NP + NC) * 32) sparse_alpha_bwd_ws_kernel
             const float off = wnext(wscan_suffix_add(gst), 0.f);
 #pragma unroll
             for (int k = 0; k < EPT; ++k) carry[k] = (off + gsl[k]) * rc[k];
+            // (the consumer released this slot D steps ago -- implied by fullA, waited for directly so that
+            //  every write-after-read on the ring has its own barrier edge)
+            mbar_wait(&emptyC[slot], (unsigned)(((q / kWsDepth) & 1) ^ 1));
             st4(slot_arr(slot, 3), g);
             st4(slot_arr(slot, 4), carry);
             __syncwarp();
@@ -2110,6 +2113,7 @@ __global__ void __launch_bounds__((1 + NP + NC) * 32) sparse_alpha_bwd_ws_kernel
             }
             const int slot = q % kWsDepth;
             mbar_wait_relaxed(&emptyC[slot], (unsigned)(((q / kWsDepth) & 1) ^ 1));
+            if (q >= kWsDepth) mbar_wait_relaxed(&fullC[slot], (unsigned)(((q / kWsDepth) - 1) & 1));
             st4(slot_arr(slot, 0), ga);
             st4(slot_arr(slot, 1), mzP);
             st4(slot_arr(slot, 2), rc);
@@ -2128,6 +2132,7 @@ __global__ void __launch_bounds__((1 + NP + NC) * 32) sparse_alpha_bwd_ws_kernel
         for (int q = w; q < T_len; q += NC) {
             const int i = T_len - 1 - q;
             const int slot = q % kWsDepth;
+            mbar_wait_relaxed(&fullA[slot], (unsigned)((q / kWsDepth) & 1));
             mbar_wait_relaxed(&fullC[slot], (unsigned)((q / kWsDepth) & 1));
             float g[EPT], carry[EPT], ms[EPT], p[EPT], up[EPT], cp[EPT], rx[EPT];
             ld4(slot_arr(slot, 3), g);

@@ -184,6 +184,24 @@ def test_pooled_latency_loss_mode_without_dense_alpha(s, masked):
     assert_parity(sed.grad, seo.grad, "lean grad_energy", extra_atol=floor)
 
 
+@pytest.mark.parametrize("s,masked", [(1024, False), (1000, True), (2048, False)])
+def test_pooled_grid_kernels_are_deterministic(s, masked):
+    """The recurrence kernels of the pooled-grid path are warp-specialised: producer, chain and consumer
+    warps exchange a step's operands through shared-memory rings guarded by mbarriers.  A missing
+    ordering edge would show up as run-to-run differences; 40 repetitions must be bit-identical."""
+    n, t, ratio = 8, 96, 8
+    pp, se, ga, gb, mask = _seeded(n, t, s, ratio, 123, masked)
+    first = None
+    for _ in range(40):
+        out = _run(pp, s, ratio, se, mask, True, ga, gb, right_padding=masked)
+        torch.cuda.synchronize()
+        if first is None:
+            first = [x.clone() for x in out]
+        else:
+            for a, b in zip(first, out):
+                assert torch.equal(a, b)
+
+
 def test_pooled_without_dense_output_and_is_fused_query():
     from simulst_b200 import _lib, ops
     lib = _lib.load()
