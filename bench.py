@@ -930,7 +930,24 @@ def bench_pooled(lib, dev):
     flags = _lib.MMA_MASS_PRESERVATION | _lib.MMA_SOFT
     B16 = _lib.BF16
 
-    def step_pooled(lean):
+    gm = torch.Generator().manual_seed(1236)
+    lens = torch.randint(S // 2, S + 1, (N_ROWS,), generator=gm)
+    mask = (torch.arange(S)[None, :] >= lens[:, None]).to(dev).view(torch.uint8).contiguous()
+
+    def step_pooled(lean, masked=False):
+        mk = mask.data_ptr() if masked else None
+        fl = flags | (_lib.MMA_RIGHT_PADDING if masked else 0)
+        if masked:
+            rc = lib.simulst_mma_train_fwd_pooled(pp.data_ptr(), B16, ratio, e.data_ptr(), B16, mk, None,
+                                                  alpha.data_ptr(), beta.data_ptr(), side.data_ptr(), None,
+                                                  ws.data_ptr(), N_ROWS, T, S, EPS, 0, fl, status.data_ptr(), st)
+            _lib.check(rc, "simulst_mma_train_fwd_pooled")
+            rc = lib.simulst_mma_train_bwd_pooled(pp.data_ptr(), B16, ratio, e.data_ptr(), B16, mk, None,
+                                                  None, side.data_ptr(), ga.data_ptr(), gb.data_ptr(), None,
+                                                  gpp.data_ptr(), B16, None, ge.data_ptr(), B16, ws.data_ptr(),
+                                                  N_ROWS, T, S, EPS, 0, fl, st)
+            _lib.check(rc, "simulst_mma_train_bwd_pooled")
+            return
         rc = lib.simulst_mma_train_fwd_pooled(pp.data_ptr(), B16, ratio, e.data_ptr(), B16, None, None,
                                               None if lean else alpha.data_ptr(), beta.data_ptr(), side.data_ptr(),
                                               delays.data_ptr() if lean else None, ws.data_ptr(),
@@ -942,7 +959,18 @@ def bench_pooled(lib, dev):
                                               ge.data_ptr(), B16, ws.data_ptr(), N_ROWS, T, S, EPS, 0, flags, st)
         _lib.check(rc, "simulst_mma_train_bwd_pooled")
 
-    def step_dense(lean):
+    def step_dense(lean, masked=False):
+        if masked:
+            fl = flags | _lib.MMA_RIGHT_PADDING
+            rc = lib.simulst_mma_train_fwd(pd.data_ptr(), B16, e.data_ptr(), B16, mask.data_ptr(), alpha.data_ptr(),
+                                           beta.data_ptr(), side.data_ptr(), N_ROWS, T, S, EPS, 0, fl,
+                                           status.data_ptr(), st)
+            _lib.check(rc, "simulst_mma_train_fwd")
+            rc = lib.simulst_mma_train_bwd(pd.data_ptr(), B16, e.data_ptr(), B16, mask.data_ptr(), alpha.data_ptr(),
+                                           side.data_ptr(), ga.data_ptr(), gb.data_ptr(), gpd.data_ptr(), B16,
+                                           ge.data_ptr(), B16, N_ROWS, T, S, EPS, 0, fl, st)
+            _lib.check(rc, "simulst_mma_train_bwd")
+            return
         rc = lib.simulst_mma_train_fwd_delays(pd.data_ptr(), B16, e.data_ptr(), B16, None, alpha.data_ptr(),
                                               beta.data_ptr(), side.data_ptr(), delays.data_ptr() if lean else None,
                                               N_ROWS, T, S, EPS, 0, flags, status.data_ptr(), st)
@@ -976,6 +1004,15 @@ def bench_pooled(lib, dev):
                      "value": elems / (us_p * 1e-6), "speedup_vs_dense_kernels": us_d / us_p,
                      "algorithmic_bytes_per_element": bytes_f + bytes_b,
                      "roofline_frac": elems * (bytes_f + bytes_b) / (us_p * 1e-6) / 1e9 / peak}
+    # right-padded batch (lengths ~ U[S/2, S], the masked_batch entry's mask) with the right-padding promise
+    for _ in range(3):
+        step_pooled(False, True)
+        step_dense(False, True)
+    torch.cuda.synchronize()
+    us_p = _events_us(lambda: step_pooled(False, True), 10)
+    us_d = _events_us(lambda: step_dense(False, True), 10)
+    out["right_padded_batch"] = {"pooled_us_per_step": us_p, "dense_kernels_on_expanded_tensor_us_per_step": us_d,
+                                 "value": elems / (us_p * 1e-6), "speedup_vs_dense_kernels": us_d / us_p}
     out["value"] = out["full_outputs"]["value"]
     return out
 
