@@ -217,3 +217,24 @@ def test_cif_tile_kernels_equal_per_warp_kernels(b, s, c, beta, train, dtype):
         lib.simulst_cif_set_tile(1)
     for got, want, what in zip(outs[0], outs[1], ("cif_out", "delays", "lengths", "grad_input", "grad_alpha")):
         assert torch.equal(got, want), what
+
+
+def test_cif_function_accepts_host_resident_target_lengths():
+    """Extension over the reference: target_lengths on the host give T without the device read of
+    cif.py:72; results are identical to the call with the lengths on the device."""
+    import torch
+    from simulst_b200.models.torch_cif import cif_function
+    g = torch.Generator().manual_seed(77)
+    b, s, c = 5, 90, 24
+    x = torch.randn(b, s, c, generator=g).to("cuda")
+    a = torch.sigmoid(torch.randn(b, s, generator=g) - 1.0).to("cuda")
+    tl = a.sum(1).round().clamp(min=1).long()
+    xa, aa = x.clone().requires_grad_(), a.clone().requires_grad_()
+    xb, ab = x.clone().requires_grad_(), a.clone().requires_grad_()
+    ra = cif_function(xa, aa, target_lengths=tl)
+    rb = cif_function(xb, ab, target_lengths=tl.cpu())
+    for key in ("cif_out", "cif_lengths", "alpha_sum", "delays"):
+        assert torch.equal(ra[key][0], rb[key][0]), key
+    ra["cif_out"][0].square().sum().backward()
+    rb["cif_out"][0].square().sum().backward()
+    assert torch.equal(xa.grad, xb.grad) and torch.equal(aa.grad, ab.grad)
