@@ -40,7 +40,7 @@ namespace simulst {
 
 namespace {
 
-// development knob (SIMULST_SPARSE_VARIANT): 0 warp-specialised K1/K4 (default), 1 single-warp pipelined, 2 generic
+// development knob (SIMULST_SPARSE_VARIANT): 0 warp-specialised K1/K4 (default), 2 generic block-scan kernels
 static const int g_sparse_variant = [] { const char* e = getenv("SIMULST_SPARSE_VARIANT"); return e ? atoi(e) : 0; }();
 
 constexpr float kLog2eS = 1.4426950408889634f;
@@ -1232,516 +1232,6 @@ __global__ void __launch_bounds__(NW * 32) sparse_alpha_bwd_kernel(const SparseP
 
 
 // =============================================================================================
-// K1 / K4 for rows whose grid fits ONE WARP (Sp <= 32 * EPT; S <= 2048 at ratio 8): no barriers,
-// and the scans of consecutive steps that do not depend on each other advance level by level in
-// one instruction stream, so a step costs about one shuffle-scan latency instead of four.
-//   K1: the cumprod scan of step i+1 rides with the recurrence scan of step i; the row sums
-//       (mass preservation, expected delays) are not reduced per step at all -- per-lane partial
-//       sums of 32 steps go to shared memory and lane j reduces step j.
-//   K4: four steps in flight (A1 cumprod scan of step c-2, A2 u-prefix scan of step c-1, B the
-//       recurrence-gradient suffix scan of step c -- the only chain carried between steps -- and
-//       C the exclusive suffix scan that finishes the gradient of step c+1).
-__device__ __forceinline__ void wscan_mul_add(float& xm, float& ua, int) { wscan_xu(xm, ua); }
-// prefix product, prefix sum and two suffix sums, level by level
-template <int D>
-__device__ __forceinline__ void scan_level_w4(float& x, float& u, float& a, float& b) {
-    asm volatile("{\n\t.reg .f32 t0, t1, t2, t3;\n\t.reg .pred q0, q1;\n\t"
-        "shfl.sync.up.b32 t0|q0, %0, %4, 0, 0xffffffff;\n\t"
-        "shfl.sync.up.b32 t1, %1, %4, 0, 0xffffffff;\n\t"
-        "shfl.sync.down.b32 t2|q1, %2, %4, 31, 0xffffffff;\n\t"
-        "shfl.sync.down.b32 t3, %3, %4, 31, 0xffffffff;\n\t"
-        "@q0 mul.rn.f32 %0, %0, t0;\n\t"
-        "@q0 add.rn.f32 %1, %1, t1;\n\t"
-        "@q1 add.rn.f32 %2, %2, t2;\n\t"
-        "@q1 add.rn.f32 %3, %3, t3;\n\t}"
-        : "+f"(x), "+f"(u), "+f"(a), "+f"(b)
-        : "n"(D));
-}
-__device__ __forceinline__ void wscan_4(float& xm, float& ua, float& s1, float& s2, int) {
-    scan_level_w4<1>(xm, ua, s1, s2); scan_level_w4<2>(xm, ua, s1, s2); scan_level_w4<4>(xm, ua, s1, s2);
-    scan_level_w4<8>(xm, ua, s1, s2); scan_level_w4<16>(xm, ua, s1, s2);
-}
-
-// Operands of the single-warp kernels come through a shared-memory ring of step CHUNKS filled by
-// TMA bulk copies (a single warp cannot hide a DRAM latency per step any other way): kW1Chunk
-// steps per chunk, kW1Slots chunks resident.  Needs T*Sp*esize to be a multiple of 16 bytes.
-constexpr int kW1Chunk = 8, kW1Slots = 3;
-
-template <int EPT, typename T>
-__global__ void __launch_bounds__(32) sparse_alpha_fwd_w1_kernel(const SparseParams prm) {
-    constexpr int CAPP = 32 * EPT;                      // pooled elements per row slot
-    __shared__ __align__(128) T ring[kW1Slots][kW1Chunk][CAPP];
-    __shared__ __align__(8) uint64_t bars[kW1Slots];
-    __shared__ float part_a[32][33], part_w[32][33];
-    __shared__ float raw_mp[32];
-    __shared__ int sh_int[2];
-    const int lane = threadIdx.x;
-    const int n = blockIdx.x;
-    const int S = prm.S, Sp = prm.Sp, r = prm.r, T_len = prm.T;
-    const float eps = prm.eps;
-    const bool mp = (prm.flags & SIMULST_MMA_MASS_PRESERVATION) != 0u;
-    const bool replace = prm.mask == nullptr;
-
-    const RowGeom geo = row_geometry<32>(prm, n, sh_int);
-    if (lane == 0) { prm.lens[n] = geo.L; prm.xcol[n] = geo.xcol; }
-    float* asp = prm.a_sp + (size_t)n * T_len * Sp;
-    float* ax = prm.a_x + (size_t)n * T_len;
-    float4* info = prm.mp_info + (size_t)n * T_len;
-    if (geo.L < 0) {
-        if (lane == 0 && prm.status != nullptr) atomicOr(prm.status, SIMULST_ST_NOT_RIGHT_PADDED);
-        const float qnan = __int_as_float(0x7fc00000);
-        for (size_t q = lane; q < (size_t)T_len * Sp; q += 32) asp[q] = qnan;
-        for (int q = lane; q < T_len; q += 32) { ax[q] = qnan; info[q] = make_float4(0.f, 0.f, 0.f, 0.f); }
-        return;
-    }
-    const int L = geo.L;
-    const int m0 = lane * EPT;
-    float W[EPT], wcolm[EPT], summ[EPT];
-    bool valid[EPT], live[EPT];
-    const double log1e = log((double)(1.0f + eps));
-    const bool has_res = mp && (geo.mp_m >= 0 || geo.xcol >= 0);
-    const int k_mp = (mp && geo.mp_m >= m0 && geo.mp_m < m0 + EPT) ? geo.mp_m - m0 : -1;
-#pragma unroll
-    for (int k = 0; k < EPT; ++k) {
-        const int m = m0 + k;
-        valid[k] = m < Sp;
-        const int col = valid[k] ? grid_col(m, Sp, S, r) : 0;
-        live[k] = valid[k] && col < L;
-        W[k] = valid[k] ? (float)exp((double)(1 + col - m) * log1e) : 1.0f;
-        const bool excl = replace && k == k_mp;         // REPLACE: the residual excludes the column itself
-        summ[k] = excl ? 0.f : 1.0f;
-        wcolm[k] = excl ? 0.f : (float)(col + 1);
-    }
-    const float w_mp = geo.mp_m >= 0 ? (float)(grid_col(geo.mp_m, Sp, S, r) + 1) : (float)(geo.xcol + 1);
-    const bool vec_store = (Sp % EPT) == 0;             // every lane wholly inside or outside the row, rows 16-byte aligned
-
-    // ---- chunk ring of p rows
-    const T* gpp = reinterpret_cast<const T*>(prm.pp) + (size_t)n * T_len * Sp;
-    const int n_chunks = (T_len + kW1Chunk - 1) / kW1Chunk;
-    if (lane == 0) {
-        for (int s2 = 0; s2 < kW1Slots; ++s2) mbar_init(&bars[s2], 1);
-        mbar_fence_init();
-    }
-    __syncwarp();
-    auto issue_chunk = [&](int q) {
-        if (q < n_chunks && lane == 0) {
-            const int rows = min(kW1Chunk, T_len - q * kW1Chunk);
-            uint64_t* bar = &bars[q % kW1Slots];
-            if (Sp == CAPP) {
-                mbar_expect_tx(bar, (unsigned)(rows * Sp * sizeof(T)));
-                tma_load_1d(&ring[q % kW1Slots][0][0], gpp + (size_t)q * kW1Chunk * Sp, (unsigned)(rows * Sp * sizeof(T)), bar);
-            } else {
-                mbar_expect_tx(bar, (unsigned)(rows * Sp * sizeof(T)));
-                for (int rr = 0; rr < rows; ++rr)
-                    tma_load_1d(&ring[q % kW1Slots][rr][0], gpp + ((size_t)q * kW1Chunk + rr) * Sp,
-                                (unsigned)(Sp * sizeof(T)), bar);
-            }
-        }
-    };
-    issue_chunk(0);
-    issue_chunk(1);
-
-    unsigned umax = 0u;                     // first-level prob_check: largest bit pattern seen
-    // stage A local part of step i: p -> x, local exclusive product; returns the thread total
-    float p_n[EPT], xe_n[EPT];
-    auto stage_a_local = [&](int i) -> float {
-        const int q = i / kW1Chunk, rr = i - q * kW1Chunk;
-        if (rr == 0) {
-            mbar_wait(&bars[q % kW1Slots], (unsigned)((q / kW1Slots) & 1));
-            if (q >= 1) issue_chunk(q + 1);             // the slot of chunk q-2 was last read an iteration ago
-        }
-        const T* src = &ring[q % kW1Slots][rr][m0];
-        float xt = 1.0f;
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            const T tv = src[k];
-            unsigned bitsv;
-            if constexpr (sizeof(T) == 4) bitsv = __float_as_uint(to_f32<T>(tv));
-            else bitsv = (unsigned)(*reinterpret_cast<const unsigned short*>(&tv)) << 16;
-            if (valid[k]) umax = max(umax, bitsv);
-            const float v = to_f32<T>(tv);
-            p_n[k] = live[k] ? v : 0.f;
-            xe_n[k] = xt;
-            xt *= (1.0f - p_n[k]) + eps;                // columns beyond Sp (p = 0) only follow valid ones
-        }
-        return xt;
-    };
-    float P[EPT], rc[EPT];
-    auto stage_a_finish = [&](float xoff) {
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            const float cp = W[k] * (xoff * xe_n[k]);
-            const float c = fminf(fmaxf(cp, eps), 1.0f);
-            P[k] = p_n[k] * cp;
-            rc[k] = fast_rcp(c);
-        }
-    };
-    if (T_len > 0) {            // prologue: stage A of step 0
-        float xt = stage_a_local(0);
-        float dummy = 0.f;
-        wscan_mul_add(xt, dummy, lane);
-        stage_a_finish(wprev(xt, 1.0f));
-    }
-    float a_prev[EPT];
-#pragma unroll
-    for (int k = 0; k < EPT; ++k) a_prev[k] = (S == 1 && m0 + k == 0) ? 1.0f : 0.0f;
-
-    auto post_pass = [&](int base, int count) {
-        // lane j finishes step base + j: row sums, residual, side values, expected delay, and the
-        // mass-preservation column of the stored row
-        __syncwarp();
-        if (lane < count) {
-            const int i = base + lane;
-            float sa = 0.f, sw = 0.f;
-#pragma unroll 8
-            for (int l = 0; l < 32; ++l) { sa += part_a[lane][l]; sw += part_w[lane][l]; }
-            float res = 0.f;
-            if (has_res) res = 1.0f - fminf(fmaxf(sa, 0.0f), 1.0f);
-            const float raw_v = geo.mp_m >= 0 ? raw_mp[lane] : 0.f;
-            if (mp && prm.side != nullptr) {
-                prm.side[((size_t)n * T_len + i) * 2] = raw_v;
-                prm.side[((size_t)n * T_len + i) * 2 + 1] = sa;
-            }
-            info[i] = make_float4(sa, raw_v, 0.f, 0.f);
-            if (mp && geo.mp_m >= 0) asp[(size_t)i * Sp + geo.mp_m] = replace ? res : raw_v + res;
-            ax[i] = (mp && geo.xcol >= 0) ? res : 0.f;
-            if (prm.delays != nullptr) prm.delays[(size_t)n * T_len + i] = has_res ? sw + w_mp * res : sw;
-        }
-        __syncwarp();
-    };
-
-    for (int i = 0; i < T_len; ++i) {
-        // ---- local parts: B(i) and A(i+1)
-        float P_c[EPT], u[EPT], ut = 0.f;
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            P_c[k] = P[k];
-            ut += a_prev[k] * rc[k];
-            u[k] = ut;
-        }
-        float xt = 1.0f;
-        if (i + 1 < T_len) xt = stage_a_local(i + 1);
-        // ---- both scans level by level
-        wscan_mul_add(xt, ut, lane);
-        const float xoff = wprev(xt, 1.0f);
-        const float uoff = wprev(ut, 0.f);
-        // ---- B(i): alpha of step i
-        const float s_off = uoff + ((i == 0 && S != 1) ? 1.0f : 0.0f);
-        float a[EPT], pa = 0.f, pw = 0.f;
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            const float z = P_c[k] * (s_off + u[k]);
-            a[k] = fminf(fmaxf(z, 0.0f), 1.0f);
-            a_prev[k] = a[k];
-            pa += a[k] * summ[k];
-            pw += a[k] * wcolm[k];
-        }
-        if (i + 1 < T_len) stage_a_finish(xoff);
-        float* arow = asp + (size_t)i * Sp + m0;
-        if (k_mp >= 0) {
-#pragma unroll
-            for (int k = 0; k < EPT; ++k)
-                if (k == k_mp) raw_mp[i & 31] = a[k];
-        }
-        if (vec_store) {
-            // (the mass-preservation column is rewritten by post_pass, a __syncwarp later)
-            if (valid[0]) {
-#pragma unroll
-                for (int c4 = 0; c4 < EPT / 4; ++c4)
-                    *reinterpret_cast<float4*>(arow + 4 * c4) = make_float4(a[4 * c4], a[4 * c4 + 1], a[4 * c4 + 2], a[4 * c4 + 3]);
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < EPT; ++k)
-                if (valid[k]) arow[k] = a[k];
-        }
-        part_a[i & 31][lane] = pa;
-        part_w[i & 31][lane] = pw;
-        if ((i & 31) == 31 || i == T_len - 1) post_pass(i & ~31, (i & 31) + 1);
-    }
-    // ---- prob_check (functions.py:9-17) / safe_cumprod's sign check: bit patterns above 1.0f are
-    // NaN, > 1, or negative; the exact classification only runs when the cheap test trips
-    if (prm.status != nullptr) {
-        unsigned bits = 0u;
-        if (__any_sync(kFull, umax > 0x3f800000u)) {
-            for (size_t q = lane; q < (size_t)T_len * Sp; q += 32) {
-                const float v = to_f32<T>(gpp[q]);
-                bits |= prob_bits(v) | ((((1.0f - v) + eps) < 0.f) ? SIMULST_ST_NEGPROD : 0u);
-            }
-        }
-        bits = __reduce_or_sync(kFull, bits);
-        if (lane == 0 && bits) atomicOr(prm.status, bits);
-    }
-}
-
-template <int EPT, typename T>
-__global__ void __launch_bounds__(32) sparse_alpha_bwd_w1_kernel(const SparseParams prm) {
-    constexpr int CAPP = 32 * EPT;
-    // ring of step chunks: p, alpha on the grid, dL/d alpha' on the grid, {row sum, raw column}, g at xcol
-    extern __shared__ __align__(128) unsigned char smem_w1[];
-    constexpr int kPBytes = kW1Chunk * CAPP * (int)sizeof(T), kFBytes = kW1Chunk * CAPP * 4, kIBytes = kW1Chunk * 16;
-    constexpr int kSlot = kPBytes + 2 * kFBytes + 2 * kIBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_w1);
-    unsigned char* ring = smem_w1 + 128;
-    auto slot_p = [&](int q, int rr) { return reinterpret_cast<const T*>(ring + (q % kW1Slots) * kSlot) + rr * CAPP; };
-    auto slot_a = [&](int q, int rr) { return reinterpret_cast<const float*>(ring + (q % kW1Slots) * kSlot + kPBytes) + rr * CAPP; };
-    auto slot_g = [&](int q, int rr) { return reinterpret_cast<const float*>(ring + (q % kW1Slots) * kSlot + kPBytes + kFBytes) + rr * CAPP; };
-    auto slot_i = [&](int q, int rr) { return reinterpret_cast<const float4*>(ring + (q % kW1Slots) * kSlot + kPBytes + 2 * kFBytes) + rr; };
-    auto slot_x = [&](int q, int rr) { return reinterpret_cast<const float4*>(ring + (q % kW1Slots) * kSlot + kPBytes + 2 * kFBytes + kIBytes) + rr; };
-
-    const int lane = threadIdx.x;
-    const int n = blockIdx.x;
-    const int S = prm.S, Sp = prm.Sp, r = prm.r, T_len = prm.T;
-    const float eps = prm.eps;
-    const bool mp = (prm.flags & SIMULST_MMA_MASS_PRESERVATION) != 0u;
-    const bool replace = prm.mask == nullptr;
-    const int m0 = lane * EPT;
-    T* gout = reinterpret_cast<T*>(prm.g_pp) + (size_t)n * T_len * Sp;
-
-    const int L = prm.lens[n];
-    const int xcol = prm.xcol[n];
-    if (L < 0) {
-        for (size_t q = lane; q < (size_t)T_len * Sp; q += 32) gout[q] = from_f32<T>(0.f);
-        return;
-    }
-    int mp_m = -1;
-    if (mp) {
-        if (replace) mp_m = Sp - 1;
-        else if (L > 0 && xcol < 0) mp_m = grid_idx(L - 1, Sp, S, r);
-    }
-    const bool has_mp = mp && (mp_m >= 0 || xcol >= 0);
-    float W[EPT];
-    bool valid[EPT], live[EPT];
-    const double log1e = log((double)(1.0f + eps));
-#pragma unroll
-    for (int k = 0; k < EPT; ++k) {
-        const int m = m0 + k;
-        valid[k] = m < Sp;
-        const int col = valid[k] ? grid_col(m, Sp, S, r) : 0;
-        live[k] = valid[k] && col < L;
-        W[k] = valid[k] ? (float)exp((double)(1 + col - m) * log1e) : 1.0f;
-    }
-    const int k_mp = (mp_m >= m0 && mp_m < m0 + EPT) ? mp_m - m0 : -1;
-    const int mp_lane = mp_m >= 0 ? mp_m / EPT : 0;
-    const bool vec_store = (Sp % EPT) == 0 && sizeof(T) * EPT >= 8;
-
-    const T* gpp = reinterpret_cast<const T*>(prm.pp) + (size_t)n * T_len * Sp;
-    const float* asp = prm.a_sp + (size_t)n * T_len * Sp;
-    const float* gsp = prm.g_sp + (size_t)n * T_len * Sp;
-    const float4* info = prm.mp_info + (size_t)n * T_len;
-    const float4* gx4 = prm.g_x4 + (size_t)n * T_len;
-    const int n_chunks = (T_len + kW1Chunk - 1) / kW1Chunk;
-    const int q_max = n_chunks - 1;
-    if (lane == 0) {
-        for (int s2 = 0; s2 < kW1Slots; ++s2) mbar_init(&bars[s2], 1);
-        mbar_fence_init();
-    }
-    __syncwarp();
-    auto issue_chunk = [&](int q) {
-        if (q >= 0 && lane == 0) {
-            const int rows = min(kW1Chunk, T_len - q * kW1Chunk);
-            uint64_t* bar = &bars[q % kW1Slots];
-            unsigned char* sl = ring + (q % kW1Slots) * kSlot;
-            const size_t r0 = (size_t)q * kW1Chunk;
-            mbar_expect_tx(bar, (unsigned)(rows * Sp * (sizeof(T) + 8) + rows * 32));
-            if (Sp == CAPP) {
-                tma_load_1d(sl, gpp + r0 * Sp, (unsigned)(rows * Sp * sizeof(T)), bar);
-                tma_load_1d(sl + kPBytes, asp + r0 * Sp, (unsigned)(rows * Sp * 4), bar);
-                tma_load_1d(sl + kPBytes + kFBytes, gsp + r0 * Sp, (unsigned)(rows * Sp * 4), bar);
-            } else {
-                for (int rr = 0; rr < rows; ++rr) {
-                    tma_load_1d(sl + rr * CAPP * sizeof(T), gpp + (r0 + rr) * Sp, (unsigned)(Sp * sizeof(T)), bar);
-                    tma_load_1d(sl + kPBytes + rr * CAPP * 4, asp + (r0 + rr) * Sp, (unsigned)(Sp * 4), bar);
-                    tma_load_1d(sl + kPBytes + kFBytes + rr * CAPP * 4, gsp + (r0 + rr) * Sp, (unsigned)(Sp * 4), bar);
-                }
-            }
-            tma_load_1d(sl + kPBytes + 2 * kFBytes, info + r0, (unsigned)(rows * 16), bar);
-            tma_load_1d(sl + kPBytes + 2 * kFBytes + kIBytes, gx4 + r0, (unsigned)(rows * 16), bar);
-        }
-    };
-    issue_chunk(q_max);
-    issue_chunk(q_max - 1);
-    auto in_range = [&](int j) { return j >= 0 && j < T_len; };
-
-    // ---- A1 -> A2
-    float p1[EPT], x1[EPT], cp1[EPT], rc1[EPT], pass1[EPT], P1[EPT];
-    // ---- A2 -> B
-    float p2[EPT], x2[EPT], cp2[EPT], rc2[EPT], pass2[EPT], P2[EPT], u2[EPT], s2[EPT];
-    // ---- B -> C
-    float x3[EPT], cp3[EPT], gP3[EPT], gcp3[EPT];
-    float carry[EPT];
-#pragma unroll
-    for (int k = 0; k < EPT; ++k) {
-        carry[k] = 0.f;
-        p1[k] = x1[k] = cp1[k] = rc1[k] = pass1[k] = P1[k] = 0.f;
-        p2[k] = x2[k] = cp2[k] = rc2[k] = pass2[k] = P2[k] = u2[k] = s2[k] = 0.f;
-        x3[k] = 1.0f; cp3[k] = gP3[k] = gcp3[k] = 0.f;
-    }
-    // iteration c runs A1(c-2), A2(c-1), B(c), C(c+1)
-    for (int c = T_len + 1; c >= -1; --c) {
-        const int jA1 = c - 2, jA2 = c - 1, jB = c, jC = c + 1;
-        const bool doA1 = in_range(jA1), doA2 = in_range(jA2), doB = in_range(jB);
-        // ================= local parts
-        // ---- A1(jA1): x, local exclusive product
-        float pA[EPT], xA[EPT], xeA[EPT], xt = 1.0f;
-        if (doA1) {
-            const int q = jA1 / kW1Chunk, rr = jA1 - q * kW1Chunk;
-            if (rr == kW1Chunk - 1 || jA1 == T_len - 1) {
-                // entering chunk q from above: every stage is done with chunk q+2
-                mbar_wait(&bars[q % kW1Slots], (unsigned)(((q_max - q) / kW1Slots) & 1));
-                if (q <= q_max - 1) issue_chunk(q - 1);
-            }
-            const T* src = slot_p(q, rr) + m0;
-#pragma unroll
-            for (int k = 0; k < EPT; ++k) {
-                const float v = to_f32<T>(src[k]);
-                pA[k] = live[k] ? v : 0.f;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < EPT; ++k) pA[k] = 0.f;
-        }
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            xA[k] = (1.0f - pA[k]) + eps;
-            xeA[k] = xt;
-            xt *= xA[k];
-        }
-        // ---- A2(jA2): u = alpha_{j-1} / c, local inclusive prefix (on what A1 produced last iteration)
-        float uA[EPT], slA[EPT], ut = 0.f;
-        {
-            float am1[EPT];
-            if (doA2 && jA2 > 0) {
-                const int jr = jA2 - 1, q = jr / kW1Chunk, rr = jr - q * kW1Chunk;
-                const float* src = slot_a(q, rr) + m0;
-#pragma unroll
-                for (int k = 0; k < EPT; ++k) am1[k] = valid[k] ? src[k] : 0.f;
-                if (k_mp >= 0) {                                       // undo mass preservation on the stored row
-                    const float rawv = slot_i(q, rr)->y;
-#pragma unroll
-                    for (int k = 0; k < EPT; ++k) am1[k] = (k == k_mp) ? rawv : am1[k];
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < EPT; ++k) am1[k] = (doA2 && S == 1 && m0 + k == 0) ? 1.0f : 0.0f;
-            }
-#pragma unroll
-            for (int k = 0; k < EPT; ++k) {
-                uA[k] = am1[k] * rc1[k];
-                ut += uA[k];
-                slA[k] = ut;
-            }
-        }
-        // ---- B(jB): g = ga + carry ; gz ; gP ; gs, local inclusive suffix
-        float gPB[EPT], gslB[EPT], gst = 0.f;
-        {
-            float G[EPT], gmp = 0.f;
-            if (doB) {
-                const int q = jB / kW1Chunk, rr = jB - q * kW1Chunk;
-                const float* src = slot_g(q, rr) + m0;
-#pragma unroll
-                for (int k = 0; k < EPT; ++k) G[k] = live[k] ? src[k] : 0.f;
-                if (has_mp) {
-                    float cand;
-                    if (xcol >= 0) {
-                        cand = slot_x(q, rr)->x;
-                    } else {
-                        float own = 0.f;
-#pragma unroll
-                        for (int k = 0; k < EPT; ++k) own = (k == k_mp) ? G[k] : own;
-                        cand = __shfl_sync(kFull, own, mp_lane);
-                    }
-                    const float ssum = slot_i(q, rr)->x;
-                    gmp = (ssum >= 0.0f && ssum <= 1.0f) ? cand : 0.f;
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < EPT; ++k) G[k] = 0.f;
-            }
-#pragma unroll
-            for (int k = EPT - 1; k >= 0; --k) {
-                const float z = P2[k] * s2[k];
-                float ga = G[k] - gmp;
-                if (replace && k == k_mp) ga = 0.f;
-                const float g = (doB && live[k]) ? ga + carry[k] : 0.f;
-                const float gz = (z >= 0.0f && z <= 1.0f) ? g : 0.f;
-                gPB[k] = gz * s2[k];
-                gst += gz * P2[k];
-                gslB[k] = gst;
-            }
-        }
-        // ---- C(jC): gA = gcp * cp, local exclusive suffix
-        float gAlC[EPT], gAt = 0.f;
-#pragma unroll
-        for (int k = EPT - 1; k >= 0; --k) {
-            gAlC[k] = gAt;
-            gAt += gcp3[k] * cp3[k];
-        }
-        // ================= the four scans, level by level
-        wscan_4(xt, ut, gst, gAt, lane);
-        const float xoff = wprev(xt, 1.0f);
-        const float uoff = wprev(ut, 0.f);
-        const float gsoff = wnext(gst, 0.f);
-        const float gAoff = wnext(gAt, 0.f);
-        // ================= finish
-        // ---- C(jC): gradient of the pooled p_choose of step jC
-        if (in_range(jC)) {
-            T* orow = gout + (size_t)jC * Sp + m0;
-            __align__(16) T ov[EPT];
-#pragma unroll
-            for (int k = 0; k < EPT; ++k) {
-                const float o = gP3[k] * cp3[k] - (gAoff + gAlC[k]) * fast_rcp(x3[k]);
-                ov[k] = from_f32<T>(live[k] ? o : 0.f);
-            }
-            if (vec_store) {
-                if (valid[0]) {
-                    if constexpr (sizeof(T) * EPT == 8) {
-                        *reinterpret_cast<uint2*>(orow) = *reinterpret_cast<const uint2*>(ov);
-                    } else {
-#pragma unroll
-                        for (int c4 = 0; c4 < (int)(sizeof(T) * EPT / 16); ++c4)
-                            reinterpret_cast<uint4*>(orow)[c4] = reinterpret_cast<const uint4*>(ov)[c4];
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < EPT; ++k)
-                    if (valid[k]) orow[k] = ov[k];
-            }
-        }
-        // ---- B(jB): carry for step jB-1; hand gP, gcp to C
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            const float gu = gsoff + gslB[k];
-            carry[k] = doB ? gu * rc2[k] : carry[k];
-            x3[k] = x2[k]; cp3[k] = cp2[k]; gP3[k] = gPB[k];
-            gcp3[k] = gPB[k] * p2[k] - (carry[k] * u2[k]) * pass2[k];
-        }
-        // ---- A2(jA2): s, hand everything to B
-        {
-            const float s_off = uoff + ((jA2 == 0 && S != 1) ? 1.0f : 0.0f);
-#pragma unroll
-            for (int k = 0; k < EPT; ++k) {
-                p2[k] = p1[k]; x2[k] = x1[k]; cp2[k] = cp1[k]; rc2[k] = rc1[k]; pass2[k] = pass1[k]; P2[k] = P1[k];
-                u2[k] = uA[k];
-                s2[k] = s_off + slA[k];
-            }
-        }
-        // ---- A1(jA1): cp, clamp, 1/c, pass mask, P
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            const float cp = W[k] * (xoff * xeA[k]);
-            const float cc = fminf(fmaxf(cp, eps), 1.0f);
-            p1[k] = pA[k]; x1[k] = xA[k]; cp1[k] = cp;
-            rc1[k] = fast_rcp(cc);
-            pass1[k] = (cc == cp) ? 1.0f : 0.0f;
-            P1[k] = pA[k] * cp;
-        }
-    }
-}
-
-
-// =============================================================================================
 // K1 / K4, warp-specialised (rows whose grid fits one warp: Sp <= 32 * EPT).  A single warp that
 // does everything issues ~240 (forward) / ~500 (backward) instructions per step in order, at one
 // instruction per ~4.4 cycles: the recurrence waits behind work that does not depend on it.  Here
@@ -2240,33 +1730,6 @@ int launch_alpha(const SparseParams& prm, bool bwd, cudaStream_t st) {
         }
         if (which == 0) k4<<<prm.N, 6 * 32, smem, st>>>(prm);
         else k8<<<prm.N, 6 * 32, smem, st>>>(prm);
-        return check_launch();
-    }
-    // single-warp pipelined kernels with TMA chunk rings (development comparison, variant 1)
-    if (Sp <= 256 && g_sparse_variant == 1 && ((size_t)prm.T * Sp * sizeof(T)) % 16 == 0 &&
-        ((size_t)Sp * sizeof(T)) % 16 == 0 && (reinterpret_cast<uintptr_t>(prm.pp) % 16) == 0) {
-        if (!bwd) {
-            if (Sp <= 128) sparse_alpha_fwd_w1_kernel<4, T><<<prm.N, 32, 0, st>>>(prm);
-            else sparse_alpha_fwd_w1_kernel<8, T><<<prm.N, 32, 0, st>>>(prm);
-            return check_launch();
-        }
-        static bool attr_done[2][64] = {};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        const int which = Sp <= 128 ? 0 : 1;
-        const int capp = which == 0 ? 128 : 256;
-        const size_t smem = 128 + (size_t)kW1Slots * (kW1Chunk * capp * (sizeof(T) + 8) + 2 * kW1Chunk * 16);
-        auto k4 = sparse_alpha_bwd_w1_kernel<4, T>;
-        auto k8 = sparse_alpha_bwd_w1_kernel<8, T>;
-        if (!attr_done[which][dev & 63]) {
-            if (cudaFuncSetAttribute(which == 0 ? k4 : k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-                cudaGetLastError();
-                return SIMULST_E_LAUNCH;
-            }
-            attr_done[which][dev & 63] = true;
-        }
-        if (which == 0) k4<<<prm.N, 32, smem, st>>>(prm);
-        else k8<<<prm.N, 32, smem, st>>>(prm);
         return check_launch();
     }
     if (Sp <= 128) SIMULST_SP_ALPHA(1, 4)

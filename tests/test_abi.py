@@ -50,3 +50,18 @@ def test_no_cpu_fallback():
         expected_alignment_from_p_choose(torch.rand(1, 2, 8))
     with pytest.raises(simulst_b200.BackendUnavailable):
         cif_function(torch.rand(1, 4, 2), torch.rand(1, 4))
+
+
+def test_multimem_allreduce_rejects_bad_arguments_without_touching_the_device():
+    """simulst_multimem_allreduce_f32 validates on the host before any CUDA call: null buffer, rank outside
+    the world, a length that is not a multiple of 4 floats, a misaligned multicast address."""
+    from simulst_b200 import _lib
+    lib = _lib.load()
+    assert lib.simulst_multimem_allreduce_f32(None, 1024, 0, 2, 2, None) == -1
+    assert lib.simulst_multimem_allreduce_f32(4096, 1024, 2, 2, 2, None) == -1
+    assert lib.simulst_multimem_allreduce_f32(4096, 1024, 0, 2, 0, None) == -1
+    assert lib.simulst_multimem_allreduce_f32(4096, 1022, 0, 2, 2, None) == -5
+    assert lib.simulst_multimem_allreduce_f32(4100, 1024, 0, 2, 2, None) == -5
+    assert lib.simulst_multimem_allreduce_f32(4096, 0, 0, 2, 2, None) == 0
+    assert lib.simulst_mma_pooled_workspace_bytes(512, 128, 1024, 8) > 2 * 512 * 128 * 128 * 4
+    assert lib.simulst_mma_pooled_workspace_bytes(1, 1, 0, 8) < 0
