@@ -204,3 +204,43 @@ def test_mass_preservation_left_padding(fused):
     assert torch.equal(c.p, p) and torch.equal(c.mask, mask)
     assert_parity(alpha, c.alpha, "left-padding alpha vs golden")
     assert_parity(p_d.grad, c.grad_p, "left-padding grad_p vs golden", extra_atol=2e-6 * float(ga.abs().max()))
+
+
+def _random_dense_cases(count, seed):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(count):
+        s = int(torch.randint(1, 4300, (1,), generator=g))
+        kind = int(torch.randint(0, 3, (1,), generator=g))
+        if kind == 1:
+            s = max(8, s // 8 * 8)          # rows the dense bulk-copy kernels take
+        t = int(torch.randint(1, 5, (1,), generator=g))
+        n = int(torch.randint(1, 4, (1,), generator=g))
+        masked = bool(int(torch.randint(0, 2, (1,), generator=g)))
+        dtype = [torch.float32, torch.bfloat16][int(torch.randint(0, 2, (1,), generator=g))]
+        out.append((n, t, s, masked, dtype))
+    return out
+
+
+@pytest.mark.parametrize("n,t,s,masked,dtype", _random_dense_cases(40, 77), ids=lambda v: str(v).replace("torch.", ""))
+def test_random_source_lengths_match_oracle(n, t, s, masked, dtype):
+    """Seeded random source lengths 1..4300 -- every CTA size, rows that are and are not 16-byte multiples
+    (bulk copies of the aligned superset), ragged tails, right-padded masks -- against the oracle."""
+    p, se, _, ga, gb = _seeded(n, t, s, seed=9000 + s)
+    p, se = p.to(dtype), se.to(dtype)
+    mask = None
+    if masked:
+        g = torch.Generator().manual_seed(s)
+        lens = torch.randint(1, s + 1, (n,), generator=g)
+        lens[0] = s
+        mask = torch.arange(s)[None, :] >= lens[:, None]
+    a_o, b_o, gp_o, ge_o = _oracle(p.float(), se.float(), mask, ga, gb)
+    a64, b64, gp64, ge64 = _oracle(p.float(), se.float(), mask, ga, gb, dtype64=True)
+    alpha, beta, gp, ge = _run(p, se, mask, True, 0, True, ga, gb, dtype=dtype)
+    tag = f"random dense n{n} T{t} S{s} m{int(masked)} {str(dtype)[6:]}"
+    assert_parity(alpha, a_o, tag + " alpha", a64)
+    assert_parity(beta, b_o, tag + " beta", b64)
+    floor = grad_floor(s, ga, gb)
+    rt = 1e-5 if dtype == torch.float32 else 2.0 ** -8
+    assert_parity(gp, gp_o, tag + " grad_p", gp64, rtol=rt, extra_atol=floor)
+    assert_parity(ge, ge_o, tag + " grad_energy", ge64, rtol=rt, extra_atol=floor)

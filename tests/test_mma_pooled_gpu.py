@@ -202,6 +202,63 @@ def test_pooled_grid_kernels_are_deterministic(s, masked):
                 assert torch.equal(a, b)
 
 
+def _random_pooled_cases(count, seed):
+    g = torch.Generator().manual_seed(seed)
+    cases = []
+    for _ in range(count):
+        ratio = [2, 3, 4, 8, 8, 8, 16][int(torch.randint(0, 7, (1,), generator=g))]
+        s = int(torch.randint(1, 321, (1,), generator=g))
+        if int(torch.randint(0, 2, (1,), generator=g)):
+            s = max(4, s // 4 * 4)                    # half of the cases on the pooled-grid kernels (fp32: S % 4 == 0)
+        t = int(torch.randint(1, 7, (1,), generator=g))
+        n = int(torch.randint(1, 4, (1,), generator=g))
+        masked, soft, mp = [bool(int(torch.randint(0, 2, (1,), generator=g))) for _ in range(3)]
+        cases.append((n, t, s, ratio, masked, soft, mp))
+    return cases
+
+
+@pytest.mark.parametrize("n,t,s,ratio,masked,soft,mp", _random_pooled_cases(48, 2024))
+def test_pooled_training_path_random_shapes(n, t, s, ratio, masked, soft, mp):
+    """Seeded random geometry: source lengths 1..320 (shorter than the ratio, odd, multiples of 4 and 8),
+    ratios 2..16, one to six target steps, with / without right padding (live lengths down to 1), soft
+    attention and mass preservation -- every combination against the oracle, whichever kernels serve it."""
+    import simulst_b200
+    g = torch.Generator().manual_seed(n * 1000003 + t * 10007 + s * 101 + ratio)
+    sp = (s + ratio - 1) // ratio
+    pp = torch.sigmoid(torch.randn(n, t, sp, generator=g))
+    se = torch.randn(n, t, s, generator=g) if soft else None
+    ga = torch.randn(n, t, s, generator=g)
+    gb = torch.randn(n, t, s, generator=g)
+    mask = None
+    if masked:
+        lens = torch.randint(1, s + 1, (n,), generator=g)
+        mask = torch.arange(s)[None, :] >= lens[:, None]
+    dense, alpha, beta, gpp, gse = _run(pp, s, ratio, se, mask, mp, ga, gb, right_padding=masked)
+    simulst_b200.check_status()
+    ppo = pp.clone().requires_grad_()
+    seo = se.clone().requires_grad_() if soft else None
+    p_o, a_o, b_o = omma.mma_process_train_pooled(ppo, s, ratio, seo, mask, 1e-6, mp, None)
+    loss = (a_o * ga).sum()
+    if soft:
+        loss = loss + (b_o * gb).sum()
+    loss.backward()
+    p64 = pp.double().requires_grad_()
+    s64 = se.double().requires_grad_() if soft else None
+    _, a64, b64 = omma.mma_process_train_pooled(p64, s, ratio, s64, mask, 1e-6, mp, None, compute_dtype=torch.float64)
+    l64 = (a64 * ga.double()).sum()
+    if soft:
+        l64 = l64 + (b64 * gb.double()).sum()
+    l64.backward()
+    tag = f"random pooled n{n} t{t} s{s} r{ratio} m{int(masked)} soft{int(soft)} mp{int(mp)}"
+    assert torch.equal(dense.cpu(), p_o.detach())
+    assert_parity(alpha, a_o, tag + " alpha", a64)
+    assert_parity(beta, b_o, tag + " beta", b64)
+    floor = 4e-7 * s * float(max(ga.abs().max(), gb.abs().max()))
+    assert_parity(gpp, ppo.grad, tag + " grad_p_pooled", p64.grad, extra_atol=floor)
+    if soft:
+        assert_parity(gse, seo.grad, tag + " grad_energy", s64.grad, extra_atol=floor)
+
+
 def test_pooled_without_dense_output_and_is_fused_query():
     from simulst_b200 import _lib, ops
     lib = _lib.load()
