@@ -415,6 +415,13 @@ int simulst_mma_step(const void* p_choose, int p_dtype,
                      void* alpha, void* beta,
                      int R, int S, unsigned flags, void* stream);
 
+/* Sizes the caller needs for the CIF calls below (the library never allocates):
+ *   simulst_cif_workspace_bytes(B, S)   bytes of the `workspace` argument of simulst_cif_bwd
+ *   simulst_cif_seg_stride(training, t_cap, S, beta)   minimum row stride (in int32) of `seg_first`:
+ *       training: t_cap + 2 with t_cap = max target length; inference: floor(S / beta) + 3 */
+long long simulst_cif_workspace_bytes(int B, int S);
+int simulst_cif_seg_stride(int training, int t_cap, int S, float beta);
+
 /* ---------------------------------------------------------------------------------------
  * CIF (continuous integrate-and-fire).  Replaces cif_function
  * (codebase/models/torch_cif/cif.py:23-196) with a plan pass + a gather pass (+ two backward

@@ -103,6 +103,8 @@ SIGNATURES = {
     "simulst_p_choose": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p]),
     "simulst_mma_step": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_int, c_int, c_uint, c_void_p]),
+    "simulst_cif_workspace_bytes": (c_longlong, [c_int, c_int]),
+    "simulst_cif_seg_stride": (c_int, [c_int, c_int, c_int, c_float]),
     "simulst_cif_plan": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_int,

@@ -490,6 +490,17 @@ int simulst_cif_set_tile_rows(int fwd_chunk_frames, int bwd_tile_frames) {
     return SIMULST_OK;
 }
 
+long long simulst_cif_workspace_bytes(int B, int S) {
+    if (B < 0 || S < 0) return SIMULST_E_SHAPE;
+    return 2ll * B * S * (long long)sizeof(float);      // two fp32 rows per batch row (simulst_cif_bwd)
+}
+
+int simulst_cif_seg_stride(int training, int t_cap, int S, float beta) {
+    if (t_cap < 0 || S < 0 || !(beta > 0.f)) return SIMULST_E_ARG;
+    // slots 0..T+1 (training) / up to floor(S/beta)+1 fires plus the two sentinels (inference)
+    return training ? t_cap + 2 : (int)((float)S / beta) + 3;
+}
+
 int simulst_cif_set_tile(int enable) {
     g_cif_force_fallback = enable ? 0 : 1;
     return SIMULST_OK;

@@ -550,7 +550,7 @@ class CIFFunction(torch.autograd.Function):
             if not host_lengths:
                 t_cap = int(tl.max()) if b > 0 else 0                  # host read, cif.py:72
         # segment table rows: slots 0..T+1 (training) / up to floor(S/beta)+1 fires (inference)
-        seg_stride = (t_cap + 2) if training else (int(s / beta) + 3)
+        seg_stride = int(lib.simulst_cif_seg_stride(1 if training else 0, t_cap if training else 0, s, float(beta)))
         seg_first = torch.empty((b, seg_stride), dtype=torch.int32, device=dev)
         st = _lib.stream_ptr(dev)
         with torch.cuda.device(dev):
@@ -605,7 +605,7 @@ class CIFFunction(torch.autograd.Function):
         gs = g_asum.contiguous().float() if g_asum is not None else None
         gx = torch.empty_like(x)
         ga = torch.empty_like(a)
-        ws = torch.empty(2 * b * s, dtype=torch.float32, device=dev)
+        ws = torch.empty(int(lib.simulst_cif_workspace_bytes(b, s)), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             rc = lib.simulst_cif_bwd(_lib.ptr(x), _lib.dtype_enum(x.dtype), _lib.ptr(csum), _lib.ptr(scale),
                                      _lib.ptr(a), _lib.dtype_enum(a.dtype), _lib.ptr(mask),
