@@ -179,6 +179,49 @@ int simulst_mma_train_bwd_delays(const void* p_choose, int p_dtype,
                                  void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * MMA training path with ROW PITCHES ("element strides").  Same operators and
+ * arguments as simulst_mma_train_{fwd,bwd}_delays; every [N,T,S] tensor additionally carries its
+ * row pitch `ld_*` in ELEMENTS: row (n,t) starts at element (n*T + t) * ld (so the batch stride is
+ * T * ld), ld >= S, 0 = dense (ld = S).  A tensor allocated as [N,T,ld] and used as x[..., :S] is
+ * such a tensor.  The reference has no counterpart: torch ops take strided tensors implicitly
+ * (codebase/utils/monotonic_attention.py:12-197 index [:, :, j]).
+ *
+ * Why it exists: rows are staged by 16-byte bulk copies, and a source length whose rows are not
+ * 16-byte multiples (S = 1500 in bf16, S = 999) cannot give dense tensors 16-byte rows.  When the
+ * OUTPUT tensors of a call (alpha, beta; grad_p, grad_energy) are 16-byte aligned with a pitch of
+ * at least simulst_mma_out_pitch(S) elements, the dense kernels take the call whatever the
+ * alignment of the INPUT rows: each input row is fetched as its 16-byte aligned superset and read
+ * at its byte offset, the row's tail thread masks the columns beyond S, and the padding columns
+ * [S, ld) of the outputs are written with zeros.  With dense outputs such shapes run on the generic
+ * kernels (about 2.5x slower).  Padding masks, flags, status, errors: as in the dense entry points;
+ * additionally SIMULST_E_SHAPE for a pitch below S.
+ *
+ * simulst_mma_out_pitch(S): smallest pitch (elements, a multiple of 8, >= S) that qualifies the
+ * outputs of a call with source length S for the dense kernels; equals S whenever dense outputs
+ * already qualify.  Negative SIMULST_E_* on a bad S. */
+int simulst_mma_out_pitch(int S);
+int simulst_mma_train_fwd_pitched(const void* p_choose, int p_dtype, long long ld_p,
+                                  const void* soft_energy, int e_dtype, long long ld_e,
+                                  const uint8_t* padding_mask,
+                                  float* alpha, long long ld_alpha, float* beta, long long ld_beta,
+                                  float* side, float* expected_delays,
+                                  int N, int T, int S,
+                                  float eps, int chunk_size, unsigned flags,
+                                  unsigned* status, void* stream);
+int simulst_mma_train_bwd_pitched(const void* p_choose, int p_dtype, long long ld_p,
+                                  const void* soft_energy, int e_dtype, long long ld_e,
+                                  const uint8_t* padding_mask,
+                                  const float* alpha, long long ld_alpha, const float* side,
+                                  const float* grad_alpha, long long ld_grad_alpha,
+                                  const float* grad_beta, long long ld_grad_beta,
+                                  const float* grad_expected_delays,
+                                  void* grad_p, int gp_dtype, long long ld_grad_p,
+                                  void* grad_energy, int ge_dtype, long long ld_grad_energy,
+                                  int N, int T, int S,
+                                  float eps, int chunk_size, unsigned flags,
+                                  void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Pooled p_choose producer: the MMA training path of the fixed pre-decision
  * wrappers.  Replaces FixedStrideMonotonicAttention.insert_zeros and the tail of its p_choose()
  * (codebase/modules/fixed_pre_decision.py:85-95 and :139-159) fused with the three functions of

@@ -7,7 +7,8 @@ them under the same names; the math runs in hand-written CUDA reached through th
 CUDA device is missing.
 """
 from . import _lib
-from ._lib import BackendUnavailable, assume_right_padding, check_status, set_strict  # noqa: F401
+from ._lib import (BackendUnavailable, assume_right_padding, check_status, set_pitched_outputs,  # noqa: F401
+                   set_strict)
 
 __version__ = "0.1.0"
 

@@ -58,6 +58,16 @@ SIGNATURES = {
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_int, c_void_p, c_int,
                                              c_int, c_int, c_int, c_float, c_int, c_uint, c_void_p]),
+    "simulst_mma_out_pitch": (c_int, [c_int]),
+    "simulst_mma_train_fwd_pitched": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_int, c_longlong, c_void_p,
+                                              c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p,
+                                              c_int, c_int, c_int, c_float, c_int, c_uint,
+                                              c_void_p, c_void_p]),
+    "simulst_mma_train_bwd_pitched": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_int, c_longlong, c_void_p,
+                                              c_void_p, c_longlong, c_void_p, c_void_p, c_longlong,
+                                              c_void_p, c_longlong, c_void_p,
+                                              c_void_p, c_int, c_longlong, c_void_p, c_int, c_longlong,
+                                              c_int, c_int, c_int, c_float, c_int, c_uint, c_void_p]),
     "simulst_mma_pooled_is_fused": (c_int, [c_int, c_int, c_int, c_int, c_uint, c_int]),
     "simulst_mma_pooled_workspace_bytes": (c_longlong, [c_int, c_int, c_int, c_int]),
     "simulst_mma_set_pooled_grid": (c_int, [c_int]),
@@ -228,6 +238,24 @@ def assume_right_padding(flag: bool):
 
 def right_padding_assumed() -> bool:
     return _right_padding
+
+
+_pitched_outputs = os.environ.get("SIMULST_B200_PITCHED_OUTPUTS", "1") not in ("0", "", "false", "False")
+
+
+def set_pitched_outputs(flag: bool):
+    """MMA training op, source lengths whose rows are not 16-byte multiples (src_len % 8 != 0): allocate
+    alpha / beta / the gradients with a 16-byte row pitch and return them as [..., :src_len] views of the
+    pitched buffers (default on).  The dense kernels then take such rows with shifted staging; with
+    contiguous outputs they fall back to the generic kernels (about 2.5x slower).  A consumer that needs
+    contiguous memory calls .contiguous() (one extra pass) or switches this off.
+    Env: SIMULST_B200_PITCHED_OUTPUTS=0."""
+    global _pitched_outputs
+    _pitched_outputs = bool(flag)
+
+
+def pitched_outputs() -> bool:
+    return _pitched_outputs
 
 
 def status_word(device):

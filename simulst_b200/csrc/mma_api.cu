@@ -63,7 +63,9 @@ static std::atomic<int> g_split_masked{1};     // masked calls: dense pass for r
 static bool split_masked_call(const MmaParams& prm, int mode, const Config& cfg, bool dense_enabled) {
     if (!g_split_masked.load(std::memory_order_relaxed) || !dense_enabled || prm.mask == nullptr || mode == kModeSoftCk) return false;
     if (prm.flags & (SIMULST_MMA_LEFT_PADDING | SIMULST_MMA_RIGHT_PADDING)) return false;
-    if (!prm.tma || !prm.vec_out || prm.S % cfg.vpt != 0 || cfg.threads > 512 || cfg.vpt > 12) return false;
+    if (cfg.threads > 512 || cfg.vpt > 12) return false;
+    if (prm.shift) return true;
+    if (!prm.tma || !prm.vec_out || prm.S % cfg.vpt != 0) return false;
     return true;
 }
 
@@ -146,15 +148,26 @@ struct PooledWs {
     }
 };
 
+// Row pitches (elements) of the [N,T,S] tensors of a call; 0 = dense (pitch S).
+struct Pitches {
+    long long p = 0, e = 0, alpha = 0, beta = 0, ga = 0, gb = 0, gp = 0, ge = 0;
+};
+static bool pitch_ok(long long ld, int S) { return ld == 0 || (ld >= S && ld <= (1ll << 30)); }
+static int pitch_of(long long ld, int S) { return ld == 0 ? S : (int)ld; }
+// a tensor whose every row starts on a 16-byte boundary
+static bool rows16(const void* ptr, int ld, size_t esz) { return aligned(ptr, 16) && ((size_t)ld * esz) % 16 == 0; }
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
 int mma_fwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int e_dtype,
                  const uint8_t* padding_mask, float* alpha, float* beta, float* side, float* expected_delays,
                  int N, int T, int S, float eps, int chunk_size, unsigned flags, unsigned* status, void* stream,
-                 int pool_ratio, void* p_dense, void* workspace);
+                 int pool_ratio, void* p_dense, void* workspace, const Pitches& ld = Pitches());
 int mma_bwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int e_dtype,
                  const uint8_t* padding_mask, const float* alpha, const float* side, const float* grad_alpha,
                  const float* grad_beta, const float* grad_expected_delays, void* grad_p, int gp_dtype,
                  void* grad_energy, int ge_dtype, int N, int T, int S, float eps, int chunk_size, unsigned flags,
-                 void* stream, int pool_ratio, const void* p_dense, void* grad_p_dense, void* workspace);
+                 void* stream, int pool_ratio, const void* p_dense, void* grad_p_dense, void* workspace,
+                 const Pitches& ld = Pitches());
 
 }  // namespace simulst
 
@@ -210,7 +223,7 @@ int mma_fwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
                  const uint8_t* padding_mask, float* alpha, float* beta, float* side,
                  float* expected_delays,
                  int N, int T, int S, float eps, int chunk_size, unsigned flags,
-                 unsigned* status, void* stream, int pool_ratio, void* p_dense, void* workspace) {
+                 unsigned* status, void* stream, int pool_ratio, void* p_dense, void* workspace, const Pitches& ld) {
     const bool soft = (flags & SIMULST_MMA_SOFT) != 0u;
     // the dense alpha output is optional on the pooled-grid path (soft attention only: the caller
     // then consumes alpha through beta and the expected delays)
@@ -219,6 +232,7 @@ int mma_fwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
     if (soft && (soft_energy == nullptr || beta == nullptr || e_dtype != p_dtype)) return SIMULST_E_ARG;
     if (chunk_size < 0) return SIMULST_E_ARG;
     if (N < 0 || T < 0 || S < 0 || S > SIMULST_MMA_MAX_SRC) return SIMULST_E_SHAPE;
+    if (!pitch_ok(ld.p, S) || !pitch_ok(ld.e, S) || !pitch_ok(ld.alpha, S) || !pitch_ok(ld.beta, S)) return SIMULST_E_SHAPE;
     if (N == 0 || T == 0 || S == 0) return SIMULST_OK;
     const size_t esz = dtype_size(p_dtype);
     if (!aligned(p_choose, esz) || (soft && !aligned(soft_energy, esz)) || !aligned(alpha, 4) ||
@@ -233,15 +247,32 @@ int mma_fwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
     prm.delays = expected_delays;
     prm.N = N; prm.T = T; prm.S = S; prm.eps = eps; prm.chunk = chunk_size; prm.flags = flags;
     prm.status = status;
+    prm.ld_p = pitch_of(ld.p, S); prm.ld_e = pitch_of(ld.e, S);
+    prm.ld_alpha = pitch_of(ld.alpha, S); prm.ld_beta = pitch_of(ld.beta, S);
+    prm.ld_ga = prm.ld_gb = prm.ld_gp = prm.ld_ge = S;
     const int use_pipe = g_use_pipe.load(std::memory_order_relaxed);
-    prm.tma = g_use_tma.load(std::memory_order_relaxed) && ((size_t)S * esz) % 16 == 0 &&
-              (pool_ratio > 0 || aligned(p_choose, 16)) && (!soft || aligned(soft_energy, 16));
-    prm.tma_shift = g_use_tma.load(std::memory_order_relaxed) && !prm.tma;
-    prm.vec_out = (S % 4 == 0) && aligned(alpha, 16) && (!soft || aligned(beta, 16));
+    const bool use_tma = g_use_tma.load(std::memory_order_relaxed) != 0;
+    const bool in16 = (pool_ratio > 0 || rows16(p_choose, prm.ld_p, esz)) && (!soft || rows16(soft_energy, prm.ld_e, esz));
+    prm.tma = use_tma && ((size_t)S * esz) % 16 == 0 && in16;
+    prm.tma_shift = use_tma && !prm.tma;
+    prm.vec_out = (alpha == nullptr || rows16(alpha, prm.ld_alpha, 4)) && (!soft || rows16(beta, prm.ld_beta, 4));
     prm.pipe = use_pipe & 1;
 
-    const Config cfg = pick_config(S);
+    Config cfg = pick_config(S);
     const int mode = mode_of(flags, chunk_size);
+    // Dense kernels with shifted staging (SHIFT instantiations): input rows that are not 16-byte multiples
+    // and / or S not a multiple of the per-thread element count, when the OUTPUT rows are 16-byte pitched
+    // with room for whole threads.  The CTA then keeps 16 spare columns.
+    if (use_tma && pool_ratio == 0 && prm.pipe && mode != kModeSoftCk && alpha != nullptr && S + 16 <= 6144 &&
+        (!prm.tma || S % cfg.vpt != 0) && !(flags & SIMULST_MMA_LEFT_PADDING)) {
+        const Config c2 = pick_config(S + 16);
+        const int need = round_up(S, c2.vpt);
+        if (c2.threads <= 512 && c2.vpt <= 12 && (c2.vpt < 12 || S + 32 <= 6144) && prm.vec_out && prm.ld_alpha >= need &&
+            (!soft || prm.ld_beta >= need)) {
+            cfg = c2;
+            prm.shift = 1;
+        }
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     auto run = [&](const MmaParams& q) {
         switch (p_dtype) {
@@ -277,6 +308,9 @@ int mma_fwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
         prm.tma = prm.tma && aligned(p_dense, 16);
         prm.tma_shift = g_use_tma.load(std::memory_order_relaxed) && !prm.tma;
     }
+    if (prm.mask != nullptr && prm.shift && !(flags & SIMULST_MMA_RIGHT_PADDING) &&
+        !split_masked_call(prm, mode, cfg, prm.pipe != 0))
+        prm.shift = 0;      // an arbitrary mask in a single pass: generic kernels
     if (split_masked_call(prm, mode, cfg, prm.pipe != 0)) {
         // pass 1: rows whose mask is a right-padding mask, through the dense kernels;
         // pass 2: every other row, element-by-element mask handling.  Each CTA decides from its
@@ -332,7 +366,8 @@ int mma_bwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
                  const float* grad_expected_delays,
                  void* grad_p, int gp_dtype, void* grad_energy, int ge_dtype,
                  int N, int T, int S, float eps, int chunk_size, unsigned flags,
-                 void* stream, int pool_ratio, const void* p_dense, void* grad_p_dense, void* workspace) {
+                 void* stream, int pool_ratio, const void* p_dense, void* grad_p_dense, void* workspace,
+                 const Pitches& ld) {
     const bool soft = (flags & SIMULST_MMA_SOFT) != 0u;
     const bool mp = (flags & SIMULST_MMA_MASS_PRESERVATION) != 0u;
     if (p_choose == nullptr || (alpha == nullptr && !(pool_ratio > 0 && workspace != nullptr)) || grad_p == nullptr ||
@@ -345,6 +380,9 @@ int mma_bwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
     if (mp && side == nullptr) return SIMULST_E_ARG;
     if (chunk_size < 0) return SIMULST_E_ARG;
     if (N < 0 || T < 0 || S < 0 || S > SIMULST_MMA_MAX_SRC) return SIMULST_E_SHAPE;
+    if (!pitch_ok(ld.p, S) || !pitch_ok(ld.e, S) || !pitch_ok(ld.alpha, S) || !pitch_ok(ld.ga, S) ||
+        !pitch_ok(ld.gb, S) || !pitch_ok(ld.gp, S) || !pitch_ok(ld.ge, S))
+        return SIMULST_E_SHAPE;
     if (N == 0 || T == 0 || S == 0) return SIMULST_OK;
     const size_t esz = dtype_size(p_dtype);
     if (!aligned(p_choose, esz) || !aligned(grad_p, esz) || !aligned(alpha, 4)) return SIMULST_E_ALIGN;
@@ -359,20 +397,38 @@ int mma_bwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
     prm.g_p = grad_p; prm.g_e = soft ? grad_energy : nullptr;
     prm.N = N; prm.T = T; prm.S = S; prm.eps = eps; prm.chunk = chunk_size; prm.flags = flags;
     prm.status = nullptr;
-    const bool a16 = (pool_ratio > 0 || (aligned(p_choose, 16) && aligned(grad_p, 16))) &&
-                     (!soft || aligned(soft_energy, 16)) && aligned(alpha, 16) &&
-                     (grad_alpha == nullptr || aligned(grad_alpha, 16)) &&
-                     (grad_beta == nullptr || aligned(grad_beta, 16)) &&
-                     (!soft || aligned(grad_energy, 16));
+    prm.ld_p = pitch_of(ld.p, S); prm.ld_e = pitch_of(ld.e, S); prm.ld_alpha = pitch_of(ld.alpha, S);
+    prm.ld_beta = S;
+    prm.ld_ga = pitch_of(ld.ga, S); prm.ld_gb = pitch_of(ld.gb, S);
+    prm.ld_gp = pitch_of(ld.gp, S); prm.ld_ge = pitch_of(ld.ge, S);
+    // every input row / every output row on a 16-byte boundary
+    const bool in16 = (pool_ratio > 0 || rows16(p_choose, prm.ld_p, esz)) && (!soft || rows16(soft_energy, prm.ld_e, esz)) &&
+                      (alpha == nullptr || rows16(alpha, prm.ld_alpha, 4)) &&
+                      (grad_alpha == nullptr || rows16(grad_alpha, prm.ld_ga, 4)) &&
+                      (grad_beta == nullptr || rows16(grad_beta, prm.ld_gb, 4));
+    const bool out16 = (pool_ratio > 0 || rows16(grad_p, prm.ld_gp, esz)) && (!soft || rows16(grad_energy, prm.ld_ge, esz));
     const int use_pipe = g_use_pipe.load(std::memory_order_relaxed);
-    prm.tma = g_use_tma.load(std::memory_order_relaxed) && ((size_t)S * esz) % 16 == 0 && a16;
-    prm.tma_shift = g_use_tma.load(std::memory_order_relaxed) && !prm.tma;
-    prm.vec_out = ((size_t)S * esz) % 16 == 0 && (S % 4 == 0) && a16;
+    const bool use_tma = g_use_tma.load(std::memory_order_relaxed) != 0;
+    prm.tma = use_tma && ((size_t)S * esz) % 16 == 0 && (S % 4 == 0) && in16 && out16;
+    prm.tma_shift = use_tma && !prm.tma;
+    // generic kernel: 16-byte accesses to the saved alpha rows (global loads) and the gradient rows (stores)
+    prm.vec_out = out16 && (alpha == nullptr || rows16(alpha, prm.ld_alpha, 4));
     prm.pipe = (use_pipe >> 1) & 1;
     prm.fast = (use_pipe >> 2) & 1;
 
-    const Config cfg = pick_config(S);
+    Config cfg = pick_config(S);
     const int mode = mode_of(flags, chunk_size);
+    // dense kernel with shifted staging: see mma_fwd_core
+    if (use_tma && pool_ratio == 0 && prm.fast && mode != kModeSoftCk && alpha != nullptr && S + 16 <= 6144 &&
+        (!prm.tma || S % cfg.vpt != 0) && !(flags & SIMULST_MMA_LEFT_PADDING)) {
+        const Config c2 = pick_config(S + 16);
+        const int need = round_up(S, c2.vpt);
+        if (c2.threads <= 512 && c2.vpt <= 12 && (c2.vpt < 12 || S + 32 <= 6144) && out16 && prm.ld_gp >= need &&
+            (!soft || prm.ld_ge >= need)) {
+            cfg = c2;
+            prm.shift = 1;
+        }
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     auto run = [&](const MmaParams& q) {
         switch (p_dtype) {
@@ -414,6 +470,9 @@ int mma_bwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
              : p_dtype == SIMULST_BF16 ? run_pool_gather<__nv_bfloat16>(grad_p_dense, grad_p, rows, S, Sp, pool_ratio, st)
                                        : run_pool_gather<__half>(grad_p_dense, grad_p, rows, S, Sp, pool_ratio, st);
     };
+    if (prm.mask != nullptr && prm.shift && !(flags & SIMULST_MMA_RIGHT_PADDING) &&
+        !split_masked_call(prm, mode, cfg, prm.fast != 0))
+        prm.shift = 0;
     if (split_masked_call(prm, mode, cfg, prm.fast != 0)) {
         MmaParams a = prm;          // see simulst_mma_train_fwd_delays
         a.flags |= SIMULST_MMA_RIGHT_PADDING;
@@ -429,6 +488,46 @@ int mma_bwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
 }  // namespace simulst
 
 extern "C" {
+
+int simulst_mma_out_pitch(int S) {
+    if (S <= 0 || S > SIMULST_MMA_MAX_SRC) return SIMULST_E_SHAPE;
+    const Config c1 = pick_config(S);
+    if (S + 16 > 6144) return round_up(S, c1.vpt > 8 ? c1.vpt : 8);
+    const Config c2 = pick_config(S + 16);
+    // a multiple of 8 elements (16-byte rows for every dtype) that holds whole threads of either configuration
+    int ld = round_up(S, 8);
+    while (ld < round_up(S, c1.vpt) || ld < round_up(S, c2.vpt) || ld % 8 != 0) ld += 4;
+    return ld;
+}
+
+int simulst_mma_train_fwd_pitched(const void* p_choose, int p_dtype, long long ld_p,
+                                  const void* soft_energy, int e_dtype, long long ld_e,
+                                  const uint8_t* padding_mask, float* alpha, long long ld_alpha,
+                                  float* beta, long long ld_beta, float* side, float* expected_delays,
+                                  int N, int T, int S, float eps, int chunk_size, unsigned flags,
+                                  unsigned* status, void* stream) {
+    Pitches ld;
+    ld.p = ld_p; ld.e = ld_e; ld.alpha = ld_alpha; ld.beta = ld_beta;
+    return mma_fwd_core(p_choose, p_dtype, soft_energy, e_dtype, padding_mask, alpha, beta, side, expected_delays,
+                        N, T, S, eps, chunk_size, flags, status, stream, 0, nullptr, nullptr, ld);
+}
+
+int simulst_mma_train_bwd_pitched(const void* p_choose, int p_dtype, long long ld_p,
+                                  const void* soft_energy, int e_dtype, long long ld_e,
+                                  const uint8_t* padding_mask, const float* alpha, long long ld_alpha,
+                                  const float* side, const float* grad_alpha, long long ld_grad_alpha,
+                                  const float* grad_beta, long long ld_grad_beta,
+                                  const float* grad_expected_delays,
+                                  void* grad_p, int gp_dtype, long long ld_grad_p,
+                                  void* grad_energy, int ge_dtype, long long ld_grad_energy,
+                                  int N, int T, int S, float eps, int chunk_size, unsigned flags, void* stream) {
+    Pitches ld;
+    ld.p = ld_p; ld.e = ld_e; ld.alpha = ld_alpha; ld.ga = ld_grad_alpha; ld.gb = ld_grad_beta;
+    ld.gp = ld_grad_p; ld.ge = ld_grad_energy;
+    return mma_bwd_core(p_choose, p_dtype, soft_energy, e_dtype, padding_mask, alpha, side, grad_alpha, grad_beta,
+                        grad_expected_delays, grad_p, gp_dtype, grad_energy, ge_dtype, N, T, S, eps, chunk_size,
+                        flags, stream, 0, nullptr, nullptr, nullptr, ld);
+}
 
 int simulst_mma_pooled_is_fused(int p_dtype, int S, int ratio, int chunk_size, unsigned flags, int has_mask) {
     if (!valid_dtype(p_dtype) || S <= 0 || S > SIMULST_MMA_MAX_SRC || ratio < 2) return 0;

@@ -58,14 +58,17 @@ __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : 1)) mma_
     const bool has_gb = SOFT && prm.g_beta != nullptr;
     const bool has_gd = prm.g_delays != nullptr;    // gradient of the expected delays: g'_ij += gd_i * (j+1)
 
-    const size_t row0 = (size_t)n * T_len * S;
-    const T* gp_in = reinterpret_cast<const T*>(prm.p) + row0;
-    const T* ge_in = SOFT ? reinterpret_cast<const T*>(prm.e) + row0 : nullptr;
-    const float* al = prm.alpha + row0;
-    const float* gA_in = has_ga ? prm.g_alpha + row0 : nullptr;
-    const float* gB_in = has_gb ? prm.g_beta + row0 : nullptr;
-    T* gp_out = reinterpret_cast<T*>(prm.g_p) + row0;
-    T* ge_out = SOFT ? reinterpret_cast<T*>(prm.g_e) + row0 : nullptr;
+    // row pitches in elements; the batch stride of a tensor is T * pitch
+    const int ld_p = prm.ld_p, ld_e = prm.ld_e, ld_a = prm.ld_alpha, ld_ga = prm.ld_ga, ld_gb = prm.ld_gb,
+              ld_gp = prm.ld_gp, ld_ge = prm.ld_ge;
+    const size_t nt = (size_t)n * T_len;
+    const T* gp_in = reinterpret_cast<const T*>(prm.p) + nt * ld_p;
+    const T* ge_in = SOFT ? reinterpret_cast<const T*>(prm.e) + nt * ld_e : nullptr;
+    const float* al = prm.alpha + nt * ld_a;
+    const float* gA_in = has_ga ? prm.g_alpha + nt * ld_ga : nullptr;
+    const float* gB_in = has_gb ? prm.g_beta + nt * ld_gb : nullptr;
+    T* gp_out = reinterpret_cast<T*>(prm.g_p) + nt * ld_gp;
+    T* ge_out = SOFT ? reinterpret_cast<T*>(prm.g_e) + nt * ld_ge : nullptr;
     const float* side = mp ? prm.side + (size_t)n * T_len * 2 : nullptr;
 
     Xchg xc(xraw);
@@ -127,22 +130,22 @@ __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : 1)) mma_
                 unsigned bytes = t_bytes + (SOFT ? t_bytes : 0u) + (i > 0 ? f_bytes : 0u) +
                                  (has_ga ? f_bytes : 0u) + (has_gb ? f_bytes : 0u);
                 mbar_expect_tx(&bars[s], bytes);
-                tma_load_1d(st_ptr(s, plan.off_p), gp_in + (size_t)i * S, t_bytes, &bars[s]);
-                if (SOFT) tma_load_1d(st_ptr(s, plan.off_e), ge_in + (size_t)i * S, t_bytes, &bars[s]);
-                if (i > 0) tma_load_1d(st_ptr(s, plan.off_a), al + (size_t)(i - 1) * S, f_bytes, &bars[s]);
-                if (has_ga) tma_load_1d(st_ptr(s, plan.off_ga), gA_in + (size_t)i * S, f_bytes, &bars[s]);
-                if (has_gb) tma_load_1d(st_ptr(s, plan.off_gb), gB_in + (size_t)i * S, f_bytes, &bars[s]);
+                tma_load_1d(st_ptr(s, plan.off_p), gp_in + (size_t)i * ld_p, t_bytes, &bars[s]);
+                if (SOFT) tma_load_1d(st_ptr(s, plan.off_e), ge_in + (size_t)i * ld_e, t_bytes, &bars[s]);
+                if (i > 0) tma_load_1d(st_ptr(s, plan.off_a), al + (size_t)(i - 1) * ld_a, f_bytes, &bars[s]);
+                if (has_ga) tma_load_1d(st_ptr(s, plan.off_ga), gA_in + (size_t)i * ld_ga, f_bytes, &bars[s]);
+                if (has_gb) tma_load_1d(st_ptr(s, plan.off_gb), gB_in + (size_t)i * ld_gb, f_bytes, &bars[s]);
             }
         } else if (prm.tma_shift) {
             if (tid == 0) {
                 // 16-byte aligned supersets of the (unaligned) rows; see tma_span
                 unsigned nb[5] = {0u, 0u, 0u, 0u, 0u};
                 const void* src[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-                src[0] = tma_span(gp_in + (size_t)i * S, t_bytes, nb[0]);
-                if (SOFT) src[1] = tma_span(ge_in + (size_t)i * S, t_bytes, nb[1]);
-                if (i > 0) src[2] = tma_span(al + (size_t)(i - 1) * S, f_bytes, nb[2]);
-                if (has_ga) src[3] = tma_span(gA_in + (size_t)i * S, f_bytes, nb[3]);
-                if (has_gb) src[4] = tma_span(gB_in + (size_t)i * S, f_bytes, nb[4]);
+                src[0] = tma_span(gp_in + (size_t)i * ld_p, t_bytes, nb[0]);
+                if (SOFT) src[1] = tma_span(ge_in + (size_t)i * ld_e, t_bytes, nb[1]);
+                if (i > 0) src[2] = tma_span(al + (size_t)(i - 1) * ld_a, f_bytes, nb[2]);
+                if (has_ga) src[3] = tma_span(gA_in + (size_t)i * ld_ga, f_bytes, nb[3]);
+                if (has_gb) src[4] = tma_span(gB_in + (size_t)i * ld_gb, f_bytes, nb[4]);
                 mbar_expect_tx(&bars[s], nb[0] + nb[1] + nb[2] + nb[3] + nb[4]);
                 tma_load_1d(st_ptr(s, plan.off_p), src[0], nb[0], &bars[s]);
                 if (SOFT) tma_load_1d(st_ptr(s, plan.off_e), src[1], nb[1], &bars[s]);
@@ -151,11 +154,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : 1)) mma_
                 if (has_gb) tma_load_1d(st_ptr(s, plan.off_gb), src[4], nb[4], &bars[s]);
             }
         } else {
-            coop(st_ptr(s, plan.off_p), gp_in + (size_t)i * S, sizeof(T));
-            if (SOFT) coop(st_ptr(s, plan.off_e), ge_in + (size_t)i * S, sizeof(T));
-            if (i > 0) coop(st_ptr(s, plan.off_a), al + (size_t)(i - 1) * S, 4);
-            if (has_ga) coop(st_ptr(s, plan.off_ga), gA_in + (size_t)i * S, 4);
-            if (has_gb) coop(st_ptr(s, plan.off_gb), gB_in + (size_t)i * S, 4);
+            coop(st_ptr(s, plan.off_p), gp_in + (size_t)i * ld_p, sizeof(T));
+            if (SOFT) coop(st_ptr(s, plan.off_e), ge_in + (size_t)i * ld_e, sizeof(T));
+            if (i > 0) coop(st_ptr(s, plan.off_a), al + (size_t)(i - 1) * ld_a, 4);
+            if (has_ga) coop(st_ptr(s, plan.off_ga), gA_in + (size_t)i * ld_ga, 4);
+            if (has_gb) coop(st_ptr(s, plan.off_gb), gB_in + (size_t)i * ld_gb, 4);
         }
     };
     for (int q = 0; q < NS - 1 && q < T_len; ++q) issue(q, q);
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : 1)) mma_
     float carry[VPT], a_cur[VPT];
 #pragma unroll
     for (int k = 0; k < VPT; ++k) carry[k] = 0.f;
-    if (SOFT) ld_row_f32<VPT>(al + (size_t)(T_len - 1) * S, j0, S, vec, a_cur);   // alpha'_{T-1}
+    if (SOFT) ld_row_f32<VPT>(al + (size_t)(T_len - 1) * ld_a, j0, S, vec, a_cur);   // alpha'_{T-1}
 
     int s = 0, s_fill = NS - 1;
     unsigned parity = 0u;
@@ -185,20 +188,20 @@ __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : 1)) mma_
         float p[VPT], E[VPT], am1[VPT], gA[VPT], gB[VPT];
         const bool shifted = prm.tma_shift != 0;
         lds_row_shift<T, VPT>(reinterpret_cast<const T*>(st_ptr(s, plan.off_p)),
-                              shifted ? row_shift(gp_in + (size_t)i * S) : 0, j0, p);
+                              shifted ? row_shift(gp_in + (size_t)i * ld_p) : 0, j0, p);
         if (SOFT) lds_row_shift<T, VPT>(reinterpret_cast<const T*>(st_ptr(s, plan.off_e)),
-                                        shifted ? row_shift(ge_in + (size_t)i * S) : 0, j0, E);
+                                        shifted ? row_shift(ge_in + (size_t)i * ld_e) : 0, j0, E);
         if (i > 0) {
             lds_row_shift<float, VPT>(reinterpret_cast<const float*>(st_ptr(s, plan.off_a)),
-                                      shifted ? row_shift(al + (size_t)(i - 1) * S) : 0, j0, am1);
+                                      shifted ? row_shift(al + (size_t)(i - 1) * ld_a) : 0, j0, am1);
         } else {
 #pragma unroll
             for (int k = 0; k < VPT; ++k) am1[k] = (j0 + k == 0) ? 1.0f : 0.0f;
         }
         if (has_ga) lds_row_shift<float, VPT>(reinterpret_cast<const float*>(st_ptr(s, plan.off_ga)),
-                                              shifted ? row_shift(gA_in + (size_t)i * S) : 0, j0, gA);
+                                              shifted ? row_shift(gA_in + (size_t)i * ld_ga) : 0, j0, gA);
         if (has_gb) lds_row_shift<float, VPT>(reinterpret_cast<const float*>(st_ptr(s, plan.off_gb)),
-                                              shifted ? row_shift(gB_in + (size_t)i * S) : 0, j0, gB);
+                                              shifted ? row_shift(gB_in + (size_t)i * ld_gb) : 0, j0, gB);
         if (++s == NS) { s = 0; parity ^= 1u; }
         if (++s_fill == NS) s_fill = 0;
         float a_save[VPT];          // alpha'_{i-1} exactly as stored (becomes a_cur next step)
@@ -539,7 +542,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : 1)) mma_
             const float gL = gLbase + gAl[k];
             outp[k] = is_live(k) ? (gPk[k] * cp[k] - gL * rx[k]) : 0.f;
         }
-        st_row_t<T, VPT, FULL>(gp_out + (size_t)i * S, j0, S, vec, outp);
+        st_row_t<T, VPT, FULL>(gp_out + (size_t)i * ld_gp, j0, S, vec, outp);
         if (SOFT) {
             float oute[VPT];
 #pragma unroll
@@ -548,7 +551,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : 1)) mma_
                 if (j0 + k == amax) v -= gEall;
                 oute[k] = is_live(k) ? v : 0.f;
             }
-            st_row_t<T, VPT, FULL>(ge_out + (size_t)i * S, j0, S, vec, oute);
+            st_row_t<T, VPT, FULL>(ge_out + (size_t)i * ld_ge, j0, S, vec, oute);
 #pragma unroll
             for (int k = 0; k < VPT; ++k) a_cur[k] = a_save[k];
         }

@@ -371,11 +371,18 @@ struct FastLayout {
 // DELAYS: the gradient of the expected delays is compiled in (dense rows: separate instantiation;
 // ragged rows: always compiled in, run-time flag).
 // MASKED (with RAGGED): padding_mask is a RIGHT-padding mask (the caller's promise, flag
-// SIMULST_MMA_RIGHT_PADDING): row n is live on [0, L_n).  Columns >= L_n are neutralised after
-// each load (p = 0, energy = -inf, grads = 0) -- by one thread-uniform test everywhere except in
-// the single thread the boundary falls into -- their gradients are stored as zeros, and mass
-// preservation follows the reference's right-padding rule (residual ADDED at L_n - 1).
-template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED, bool DELAYS, bool MASKED = false>
+// SIMULST_MMA_RIGHT_PADDING): row n is live on [0, L_n).  As in the forward kernel only the live bytes
+// of every row are copied, the ring slots behind them are neutral from a one-time initialisation
+// (p = 0, energy = -inf, alpha = grads = 0), and the thread that owns column L_n - 1 neutralises the
+// copy overhang of the NEXT step's rows before the step's last barrier -- the step loop itself loads
+// without per-element tests.  Gradients beyond L_n are stored as zeros, and mass preservation follows
+// the reference's right-padding rule (residual ADDED at L_n - 1).
+// SHIFT (with RAGGED and MASKED): input rows need not be 16-byte multiples and S need not be a multiple
+// of VPT -- every staged row is the 16-byte aligned superset of the real one, read at its byte offset
+// (lds_row2_sh); live length min(S, mask length), the mask optional (without one: the no-mask rule,
+// column S-1 REPLACED).  grad_p / grad_energy rows must be 16-byte pitched, pitch >= roundup(S, VPT)
+// (padding columns receive zeros); the CTA needs 16 spare columns (S + 16 <= THREADS*VPT).
+template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED, bool DELAYS, bool MASKED = false, bool SHIFT = false>
 __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS <= 160 ? 3 : (THREADS <= 256 ? 2 : 1))))
 mma_bwd_fast_kernel(const MmaParams prm) {
     constexpr int NW = THREADS / kWarp;
@@ -410,9 +417,23 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     const bool has_gd = DELAYS && prm.g_delays != nullptr;        // gradient of the expected delays: g'_ij += gd_i * (j+1)
     const bool in_row = !RAGGED || j0 < S;              // this thread's VPT columns exist
 
-    const size_t row0 = (size_t)n * T_len * S;
-    T* gp_out = reinterpret_cast<T*>(prm.g_p) + row0;
-    T* ge_out = SOFT ? reinterpret_cast<T*>(prm.g_e) + row0 : nullptr;
+    // row pitches in elements; the batch stride of a tensor is T * pitch
+    const int ld_p = prm.ld_p, ld_e = prm.ld_e, ld_a = prm.ld_alpha, ld_ga = prm.ld_ga, ld_gb = prm.ld_gb,
+              ld_gp = prm.ld_gp, ld_ge = prm.ld_ge;
+    const size_t nt = (size_t)n * T_len;
+    const T* p_in = reinterpret_cast<const T*>(prm.p) + nt * ld_p;
+    const T* e_in = SOFT ? reinterpret_cast<const T*>(prm.e) + nt * ld_e : nullptr;
+    const float* al_in = prm.alpha + nt * ld_a;
+    const float* ga_in = has_ga ? prm.g_alpha + nt * ld_ga : nullptr;
+    const float* gb_in = has_gb ? prm.g_beta + nt * ld_gb : nullptr;
+    T* gp_out = reinterpret_cast<T*>(prm.g_p) + nt * ld_gp;
+    T* ge_out = SOFT ? reinterpret_cast<T*>(prm.g_e) + nt * ld_ge : nullptr;
+    // SHIFT: byte offset of a row inside its staged aligned superset, from the low address bits
+    const unsigned p_lo = lo32(p_in), e_lo = lo32(e_in), al_lo = lo32(al_in), ga_lo = lo32(ga_in), gb_lo = lo32(gb_in);
+    const unsigned p_pitch = (unsigned)ld_p * (unsigned)sizeof(T), e_pitch = (unsigned)ld_e * (unsigned)sizeof(T),
+                   al_pitch = (unsigned)ld_a * 4u, ga_pitch = (unsigned)ld_ga * 4u, gb_pitch = (unsigned)ld_gb * 4u;
+    (void)p_lo; (void)e_lo; (void)al_lo; (void)ga_lo; (void)gb_lo;
+    (void)p_pitch; (void)e_pitch; (void)al_pitch; (void)ga_pitch; (void)gb_pitch;
     // (+ an opaque zero: the compiler must not treat the prefetched side values as uniform, or it
     // converts them to uniform registers -- and waits for the load -- right at the loop top)
     unsigned opaque_zero;
@@ -428,15 +449,20 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     }
     int live_cnt = 0;
     if (MASKED && in_row) {
-        const uint8_t* mrow = prm.mask + (size_t)n * S + j0;
+        if (SHIFT && prm.mask == nullptr) {
+            live_cnt = min(VPT, S - j0);
+        } else {
+            const uint8_t* mrow = prm.mask + (size_t)n * S + j0;
 #pragma unroll
-        for (int k = 0; k < VPT; ++k) live_cnt += (mrow[k] == 0) ? 1 : 0;
+            for (int k = 0; k < VPT; ++k)
+                if (!SHIFT || j0 + k < S) live_cnt += (mrow[k] == 0) ? 1 : 0;
+        }
     }
     if (MASKED) {
         live_cnt = __reduce_add_sync(kFull, live_cnt);
         if (lane == 0) reinterpret_cast<int*>(xs(2, 3))[warp] = live_cnt;
     }
-    if (RAGGED && !in_row) {
+    if (RAGGED && !MASKED && !in_row) {
         // neutral tails (never overwritten by the bulk copies)
         const T ninf = from_f32<T>(-INFINITY), zero = from_f32<T>(0.f);
         for (int st_i = 0; st_i < NS; ++st_i) {
@@ -467,12 +493,60 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     const int last_col = MASKED ? max(row_len - 1, 0) : S - 1;
     // owner of the mass-preservation column: dense rows REPLACE column S-1 (the last element of
     // its thread); right-padded rows ADD the residual at L-1 (any element of its thread)
+    const bool fixer = MASKED && row_len > 0 && last_col >= j0 && last_col < j0 + VPT;     // owner of the last live column
+    (void)fixer;
+    if constexpr (MASKED) {
+        if (row_len == 0) {
+            // no live column: every gradient of the row is zero
+            float zero_v[VPT];
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) zero_v[k] = 0.f;
+            if (in_row)
+                for (int i = 0; i < T_len; ++i) {
+                    st_row_t<T, VPT, true>(gp_out + (size_t)i * ld_gp, j0, S, true, zero_v);
+                    if (SOFT) st_row_t<T, VPT, true>(ge_out + (size_t)i * ld_ge, j0, S, true, zero_v);
+                }
+            return;
+        }
+        if (in_row && nl == 0) {
+            // a thread wholly beyond the row: its gradient columns are zero in every step, written here once
+            float zero_v[VPT];
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) zero_v[k] = 0.f;
+            for (int i = 0; i < T_len; ++i) {
+                st_row_t<T, VPT, true>(gp_out + (size_t)i * ld_gp, j0, S, true, zero_v);
+                if (SOFT) st_row_t<T, VPT, true>(ge_out + (size_t)i * ld_ge, j0, S, true, zero_v);
+            }
+        }
+        if (nl < VPT) {
+            // neutral ring slots from this thread's columns on (the copies rewrite the live bytes)
+            const T ninf = from_f32<T>(-INFINITY), zero = from_f32<T>(0.f);
+            for (int st_i = 0; st_i < NS; ++st_i) {
+                unsigned char* st = stage0 + st_i * L::kStage;
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) {
+                    reinterpret_cast<T*>(st + L::kOffP)[j0 + k] = zero;
+                    if (SOFT) reinterpret_cast<T*>(st + L::kOffE)[j0 + k] = ninf;
+                    reinterpret_cast<float*>(st + L::kOffGA)[j0 + k] = 0.f;
+                    if (SOFT) reinterpret_cast<float*>(st + L::kOffGB)[j0 + k] = 0.f;
+                }
+            }
+            for (int a_i = 0; a_i < NA; ++a_i)
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) reinterpret_cast<float*>(alpha0 + a_i * L::kFRow)[j0 + k] = 0.f;
+            fence_proxy_async();
+        }
+        __syncthreads();
+    }
     const bool mp_last = mp && !MASKED && j0 + VPT == S;
     const int k_add = (MASKED && mp && row_len > 0 && last_col >= j0 && last_col < j0 + VPT) ? last_col - j0 : -1;
     // weight of a column in the mass-preservation Jacobian: 0 for the REPLACED column
     const float w_lastcol = mp_last ? 0.0f : 1.0f;
+    // SHIFT rows without a mask follow the no-mask rule: the column at k_add is REPLACED, not added to
+    const bool mp_repl = SHIFT && prm.mask == nullptr;
+    (void)mp_repl;
 
-    const unsigned t_bytes = (unsigned)(S * sizeof(T)), f_bytes = (unsigned)(S * 4);
+    const unsigned t_bytes = (unsigned)((MASKED ? row_len : S) * sizeof(T)), f_bytes = (unsigned)((MASKED ? row_len : S) * 4);
     // Producers: iteration q stages step i = T-1-q into stage q % 3 and alpha slot q % 4
     // (alpha_{i-1}); the very first call also brings alpha'_{T-1} into alpha slot 3.  The five
     // bulk copies are dealt round-robin to the warps (copy j -> lane 0 of warp j % NW) so no
@@ -483,7 +557,6 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         const int s = q % NS;
         unsigned char* st = stage0 + s * L::kStage;
         uint64_t* bar = &bars[s];
-        const size_t ro = row0 + (size_t)i * S;
 #pragma unroll
         for (int w = 0; w < kIssuers; ++w) {
             if (warp == w) {                    // warp-uniform
@@ -492,15 +565,34 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                                c_ga = (3 % NW) == w, c_gb = SOFT && (4 % NW) == w;      // compile-time
                     const bool a_prev = c_a && i > 0, a_first = c_a && SOFT && q == 0;
                     const bool l_ga = c_ga && has_ga, l_gb = c_gb && has_gb;
-                    const unsigned bytes = (c_p ? t_bytes : 0u) + (c_e ? t_bytes : 0u) + (a_prev ? f_bytes : 0u) +
-                                           (a_first ? f_bytes : 0u) + (l_ga ? f_bytes : 0u) + (l_gb ? f_bytes : 0u);
-                    mbar_expect_tx(bar, bytes);
-                    if (c_p) tma_load_1d(st + L::kOffP, reinterpret_cast<const T*>(prm.p) + ro, t_bytes, bar);
-                    if (c_e) tma_load_1d(st + L::kOffE, reinterpret_cast<const T*>(prm.e) + ro, t_bytes, bar);
-                    if (a_prev) tma_load_1d(alpha0 + (q % NA) * L::kFRow, prm.alpha + ro - S, f_bytes, bar);
-                    if (a_first) tma_load_1d(alpha0 + (NA - 1) * L::kFRow, prm.alpha + ro, f_bytes, bar);
-                    if (l_ga) tma_load_1d(st + L::kOffGA, prm.g_alpha + ro, f_bytes, bar);
-                    if (l_gb) tma_load_1d(st + L::kOffGB, prm.g_beta + ro, f_bytes, bar);
+                    if constexpr (MASKED) {
+                        // the live bytes of every row (SHIFT: of its aligned superset); counts differ from row to row
+                        unsigned nb[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+                        const void* src[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+                        if (c_p) src[0] = tma_span(p_in + (size_t)i * ld_p, t_bytes, nb[0]);
+                        if (c_e) src[1] = tma_span(e_in + (size_t)i * ld_e, t_bytes, nb[1]);
+                        if (a_prev) src[2] = tma_span(al_in + (size_t)(i - 1) * ld_a, f_bytes, nb[2]);
+                        if (a_first) src[3] = tma_span(al_in + (size_t)i * ld_a, f_bytes, nb[3]);
+                        if (l_ga) src[4] = tma_span(ga_in + (size_t)i * ld_ga, f_bytes, nb[4]);
+                        if (l_gb) src[5] = tma_span(gb_in + (size_t)i * ld_gb, f_bytes, nb[5]);
+                        mbar_expect_tx(bar, nb[0] + nb[1] + nb[2] + nb[3] + nb[4] + nb[5]);
+                        if (c_p) tma_load_1d(st + L::kOffP, src[0], nb[0], bar);
+                        if (c_e) tma_load_1d(st + L::kOffE, src[1], nb[1], bar);
+                        if (a_prev) tma_load_1d(alpha0 + (q % NA) * L::kFRow, src[2], nb[2], bar);
+                        if (a_first) tma_load_1d(alpha0 + (NA - 1) * L::kFRow, src[3], nb[3], bar);
+                        if (l_ga) tma_load_1d(st + L::kOffGA, src[4], nb[4], bar);
+                        if (l_gb) tma_load_1d(st + L::kOffGB, src[5], nb[5], bar);
+                    } else {
+                        const unsigned bytes = (c_p ? t_bytes : 0u) + (c_e ? t_bytes : 0u) + (a_prev ? f_bytes : 0u) +
+                                               (a_first ? f_bytes : 0u) + (l_ga ? f_bytes : 0u) + (l_gb ? f_bytes : 0u);
+                        mbar_expect_tx(bar, bytes);
+                        if (c_p) tma_load_1d(st + L::kOffP, p_in + (size_t)i * ld_p, t_bytes, bar);
+                        if (c_e) tma_load_1d(st + L::kOffE, e_in + (size_t)i * ld_e, t_bytes, bar);
+                        if (a_prev) tma_load_1d(alpha0 + (q % NA) * L::kFRow, al_in + (size_t)(i - 1) * ld_a, f_bytes, bar);
+                        if (a_first) tma_load_1d(alpha0 + (NA - 1) * L::kFRow, al_in + (size_t)i * ld_a, f_bytes, bar);
+                        if (l_ga) tma_load_1d(st + L::kOffGA, ga_in + (size_t)i * ld_ga, f_bytes, bar);
+                        if (l_gb) tma_load_1d(st + L::kOffGB, gb_in + (size_t)i * ld_gb, f_bytes, bar);
+                    }
                 }
             }
         }
@@ -509,6 +601,9 @@ mma_bwd_fast_kernel(const MmaParams prm) {
 
     const float one_eps = 1.0f + eps;
     const float2 eps2 = f2(eps);
+    const float2 eps2x = f2((MASKED && nl == 0) ? 0.f : eps);      // no eps from the columns of a thread beyond the row
+    const float dead_eps = (MASKED && nl > 0 && nl < VPT) ? (float)(VPT - nl) * eps : 0.f;
+    (void)dead_eps;
     const float in_f = inside ? 1.0f : 0.0f;
     (void)in_f;
     // masked rows: neutralise the columns >= nl of a freshly loaded pair array
@@ -519,16 +614,67 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                 if (k >= nl) SIMULST_EL(v, k) = fill;
         }
     };
-    // max over this thread's live columns of a staged energy row
-    auto row_max = [&](const void* row) -> float {
-        if (!MASKED || nl == VPT) return lds_row_max<T, VPT>(row, j0);
-        float2 v[H];
-        lds_row2<T, VPT>(row, j0, v);
-        float mx = -INFINITY;
+    // staged row -> float2 pairs.  SHIFT: at the row's byte offset `sh` in the slot (reads clamped to the
+    // slot: threads beyond the row read neutral bytes wherever they land)
+    auto load_t = [&](const void* row, unsigned sh, float2 (&v)[H]) {
+        if constexpr (SHIFT) {
+            if (sh == 0u) lds_row2<T, VPT>(row, j0, v);         // CTA-uniform: this row happens to be aligned
+            else lds_row2_sh<T, VPT>(row, sh, j0, THREADS * VPT * (int)sizeof(T), v);
+        } else {
+            lds_row2<T, VPT>(row, j0, v);
+        }
+    };
+    auto load_f = [&](const void* row, unsigned sh, float2 (&v)[H]) {
+        if constexpr (SHIFT) {
+            if (sh == 0u) lds_row2<float, VPT>(row, j0, v);
+            else lds_row2_sh<float, VPT>(row, sh, j0, THREADS * VPT * 4, v);
+        } else {
+            lds_row2<float, VPT>(row, j0, v);
+        }
+    };
+    // MASKED: the fixer neutralises the copy overhang [L, end of the last 16-byte granule) of a landed row
+    auto fix_bytes = [&](unsigned char* slot, unsigned sh, unsigned esz, unsigned pattern) {
+        const unsigned live_end = sh + (unsigned)row_len * esz;
+        const unsigned dirt_end = (live_end + 15u) & ~15u;
+        for (unsigned o = live_end; o < dirt_end; o += esz) {
+            if (esz == 4u) *reinterpret_cast<unsigned*>(slot + o) = pattern;
+            else *reinterpret_cast<unsigned short*>(slot + o) = (unsigned short)pattern;
+        }
+        if constexpr (SHIFT) {
+            // the previous row in this slot may have started up to 15 bytes later and reached one granule further
+            if (dirt_end + 16u <= (unsigned)(THREADS * VPT) * esz) {
+                const unsigned w = esz == 4u ? pattern : (pattern | (pattern << 16));
+                *reinterpret_cast<uint4*>(slot + dirt_end) = make_uint4(w, w, w, w);
+            }
+        }
+    };
+    // all rows that arrive with producer iteration q (step i = T-1-q)
+    auto fix_stage = [&](int q) {
+        const int i = T_len - 1 - q;
+        unsigned char* st = stage0 + (q % NS) * L::kStage;
+        constexpr unsigned kNegInf = std::is_same<T, float>::value ? 0xff800000u
+                                   : (std::is_same<T, __nv_bfloat16>::value ? 0xff80u : 0xfc00u);
+        fix_bytes(st + L::kOffP, SHIFT ? sh_of(p_lo, i, p_pitch) : 0u, (unsigned)sizeof(T), 0u);
+        if (SOFT) fix_bytes(st + L::kOffE, SHIFT ? sh_of(e_lo, i, e_pitch) : 0u, (unsigned)sizeof(T), kNegInf);
+        if (has_ga) fix_bytes(st + L::kOffGA, SHIFT ? sh_of(ga_lo, i, ga_pitch) : 0u, 4u, 0u);
+        if (has_gb) fix_bytes(st + L::kOffGB, SHIFT ? sh_of(gb_lo, i, gb_pitch) : 0u, 4u, 0u);
+        if (i > 0) fix_bytes(alpha0 + (q % NA) * L::kFRow, SHIFT ? sh_of(al_lo, i - 1, al_pitch) : 0u, 4u, 0u);
+        if (SOFT && q == 0) fix_bytes(alpha0 + (NA - 1) * L::kFRow, SHIFT ? sh_of(al_lo, i, al_pitch) : 0u, 4u, 0u);
+    };
+    // max over this thread's live columns of a staged energy row (row index i_row)
+    auto row_max = [&](const void* row, int i_row) -> float {
+        float mx;
+        if constexpr (!SHIFT) {
+            mx = lds_row_max<T, VPT>(row, j0);
+        } else {
+            float2 v[H];
+            load_t(row, sh_of(e_lo, i_row, e_pitch), v);
+            mx = fmaxf(v[0].x, v[0].y);
 #pragma unroll
-        for (int k = 0; k < VPT; ++k)
-            if (k < nl) mx = fmaxf(mx, SIMULST_EL(v, k));
-        return mx;
+            for (int q = 1; q < H; ++q) mx = fmaxf(mx, fmaxf(v[q].x, v[q].y));
+        }
+        // a thread beyond the row contributes nothing (it may be looking at overhang that is not fixed yet)
+        return (MASKED && nl == 0) ? -INFINITY : mx;
     };
     float2 carry[H];
 #pragma unroll
@@ -552,9 +698,17 @@ mma_bwd_fast_kernel(const MmaParams prm) {
 
     // row max of the first step's energies (every later one is reduced one iteration ahead)
     float m_cur = 0.f, Emax_cur = -INFINITY;
+    if (MASKED && !SOFT) {
+        if (fixer) {
+            mbar_wait(&bars[0], 0u);
+            fix_stage(0);
+        }
+        __syncthreads();
+    }
     if (SOFT) {
         mbar_wait(&bars[0], 0u);
-        Emax_cur = row_max(stage0 + L::kOffE);
+        if (MASKED && fixer) fix_stage(0);
+        Emax_cur = row_max(stage0 + L::kOffE, T_len - 1);
         const float wm = warp_max(Emax_cur);
         if (lane == 0) xs(2, 2)[warp] = wm;
         __syncthreads();
@@ -584,10 +738,8 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         if (++a_slot == NA) a_slot = 0;
 
         float2 p[H], E[H];
-        lds_row2<T, VPT>(st + L::kOffP, j0, p);
-        if (SOFT) lds_row2<T, VPT>(st + L::kOffE, j0, E);
-        mask_tail(p, 0.f);
-        if (SOFT) mask_tail(E, -INFINITY);
+        load_t(st + L::kOffP, sh_of(p_lo, i, p_pitch), p);
+        if (SOFT) load_t(st + L::kOffE, sh_of(e_lo, i, e_pitch), E);
 
         // ================= X1: exclusive cumprod of (1-p)+eps ; D = eps + prefix(e) ; arg-max owner
         // (the row maximum m_cur of this step's energies was reduced during the previous
@@ -616,15 +768,17 @@ mma_bwd_fast_kernel(const MmaParams prm) {
             for (int q = 0; q < H; ++q) {
                 const float2 tt = mul2(add2(E[q], nm), l2e);
                 exm[q] = f2(ex2_approx(tt.x), ex2_approx(tt.y));
-                ex[q] = add2(exm[q], eps2);
+                ex[q] = add2(exm[q], eps2x);
                 if (RAGGED && !MASKED) ex[q] = mul2(ex[q], f2(in_f));       // no eps from columns beyond the row
             }
-            mask_tail(ex, 0.f);                                  // nor from padded columns
 #pragma unroll
             for (int q = 0; q < H; ++q) {
                 etot += ex[q].x; Dl[q].x = etot;
                 etot += ex[q].y; Dl[q].y = etot;
             }
+            // the thread the row ends in summed one eps per column beyond it (after its live columns, whose
+            // prefixes are untouched); threads wholly beyond the row have eps = 0
+            if (MASKED) etot -= dead_eps;
         }
         float xinc = xtot, einc = etot;
         if (SOFT) {
@@ -678,13 +832,24 @@ mma_bwd_fast_kernel(const MmaParams prm) {
             {
                 float2 am1[H];
                 if (i > 0) {
-                    lds_row2<float, VPT>(a_prev_row, j0, am1);
                     // undo mass preservation on the stored row: the recurrence ran on the raw alpha
-                    if (mp_last) am1[H - 1].y = side_prev_last;
-                    if (MASKED && k_add >= 0) {
-#pragma unroll
-                        for (int k = 0; k < VPT; ++k)
-                            if (k == k_add) SIMULST_EL(am1, k) = side_prev_last;
+                    if constexpr (MASKED) {
+                        // the owner of column L-1 swaps the raw value into the staged row for the duration of
+                        // its own load (the next iteration reads the same row again as alpha', unpatched)
+                        float* ap = reinterpret_cast<float*>(const_cast<unsigned char*>(a_prev_row) +
+                                                             (SHIFT ? sh_of(al_lo, i - 1, al_pitch) : 0u)) + last_col;
+                        float kept = 0.f;
+                        if (k_add >= 0) {
+                            kept = *reinterpret_cast<volatile float*>(ap);
+                            *reinterpret_cast<volatile float*>(ap) = side_prev_last;
+                        }
+                        asm volatile("" ::: "memory");
+                        load_f(a_prev_row, sh_of(al_lo, i - 1, al_pitch), am1);
+                        asm volatile("" ::: "memory");
+                        if (k_add >= 0) *reinterpret_cast<volatile float*>(ap) = kept;
+                    } else {
+                        load_f(a_prev_row, sh_of(al_lo, i - 1, al_pitch), am1);
+                        if (mp_last) am1[H - 1].y = side_prev_last;
                     }
                 } else {
 #pragma unroll
@@ -701,7 +866,7 @@ mma_bwd_fast_kernel(const MmaParams prm) {
             if (SOFT) {
                 {
                     float2 a_cur[H];
-                    lds_row2<float, VPT>(a_cur_row, j0, a_cur);
+                    load_f(a_cur_row, sh_of(al_lo, i, al_pitch), a_cur);
 #pragma unroll
                     for (int q = 0; q < H; ++q) r[q] = mul2(a_cur[q], rD[q]);
                 }
@@ -749,8 +914,7 @@ mma_bwd_fast_kernel(const MmaParams prm) {
             float2 grl[H], gB[H];
             float gtot = 0.f;
             if (has_gb) {
-                lds_row2<float, VPT>(st + L::kOffGB, j0, gB);
-                mask_tail(gB, 0.f);
+                load_f(st + L::kOffGB, sh_of(gb_lo, i, gb_pitch), gB);
             } else {
 #pragma unroll
                 for (int q = 0; q < H; ++q) gB[q] = f2(0.f);
@@ -784,9 +948,8 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         float2 gA[H];
         float gA_last = 0.f;
         if (has_ga) {
-            lds_row2<float, VPT>(st + L::kOffGA, j0, gA);
-            mask_tail(gA, 0.f);
-            if (mp) gA_last = reinterpret_cast<const float*>(st + L::kOffGA)[last_col];
+            load_f(st + L::kOffGA, sh_of(ga_lo, i, ga_pitch), gA);
+            if (mp) gA_last = reinterpret_cast<const float*>(st + L::kOffGA + (SHIFT ? sh_of(ga_lo, i, ga_pitch) : 0u))[last_col];
         } else {
 #pragma unroll
             for (int q = 0; q < H; ++q) gA[q] = f2(0.f);
@@ -819,6 +982,13 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                     const float2 wv = (q == H - 1) ? f2(1.0f, w_lastcol) : f2(1.0f);
                     g0[q] = fma2(wv, nokg, g0[q]);
                 }
+            }
+            if (SHIFT && mp_repl && k_add >= 0) {
+                // no-mask rule on a SHIFT row: the output at the REPLACED column does not depend on its raw
+                // value, which only feeds the recurrence
+#pragma unroll
+                for (int k = 0; k < VPT; ++k)
+                    if (k == k_add) SIMULST_EL(g0, k) = SIMULST_EL(carry, k);
             }
             float Atot = 0.f, Htot = 0.f;
 #pragma unroll
@@ -882,7 +1052,12 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         float Emax_next = -INFINITY;
         if (SOFT && i > 0) {
             mbar_wait(&bars[s], parity);
-            Emax_next = row_max(stage0 + s * L::kStage + L::kOffE);
+            if (MASKED && fixer) fix_stage(qi + 1);
+            Emax_next = row_max(stage0 + s * L::kStage + L::kOffE, i - 1);
+        }
+        if (MASKED && !SOFT && fixer && i > 0) {
+            mbar_wait(&bars[s], parity);
+            fix_stage(qi + 1);
         }
         float gAinc = gAtot, ws = gEsum, wmax = Emax_next;
         if (SOFT) {
@@ -902,7 +1077,7 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         int k_hit = -1;
         if (SOFT && amax == tid) {
             float2 Er[H];
-            lds_row2<T, VPT>(st + L::kOffE, j0, Er);
+            load_t(st + L::kOffE, sh_of(e_lo, i, e_pitch), Er);
 #pragma unroll
             for (int k = VPT - 1; k >= 0; --k)
                 if (SIMULST_EL(Er, k) == m) k_hit = k;
@@ -926,12 +1101,11 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                 const float2 o = fma2(mul2(gL, rx[q]), neg1, mul2(gPk[q], cp[q]));
                 outp[2 * q] = o.x; outp[2 * q + 1] = o.y;
             }
-            if (MASKED && nl < VPT) {
-#pragma unroll
-                for (int k = 0; k < VPT; ++k)
-                    if (k >= nl) outp[k] = 0.f;
+            if (MASKED ? nl > 0 : inside) st_row_t<T, VPT, true>(gp_out + (size_t)i * ld_gp, j0, S, true, outp);
+            if (MASKED && nl > 0 && nl < VPT) {
+                // the thread the row ends in: zeros over its columns beyond the row
+                for (int k = nl; k < VPT; ++k) gp_out[(size_t)i * ld_gp + j0 + k] = from_f32<T>(0.f);
             }
-            if (MASKED ? in_row : inside) st_row_t<T, VPT, true>(gp_out + (size_t)i * S, j0, S, true, outp);
         }
         if (SOFT) {
             float oute[VPT];
@@ -943,12 +1117,8 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                 for (int k = 0; k < VPT; ++k)
                     if (k == k_hit) oute[k] -= gEall;
             }
-            if (MASKED && nl < VPT) {
-#pragma unroll
-                for (int k = 0; k < VPT; ++k)
-                    if (k >= nl) oute[k] = 0.f;
-            }
-            if (MASKED ? in_row : inside) st_row_t<T, VPT, true>(ge_out + (size_t)i * S, j0, S, true, oute);
+            // (columns beyond the row: exp(-inf - m) = 0 makes their energy gradient an exact zero)
+            if (MASKED ? nl > 0 : inside) st_row_t<T, VPT, true>(ge_out + (size_t)i * ld_ge, j0, S, true, oute);
         }
         side_sum = side_sum_next;
         side_prev_last = side_prev_next;
@@ -956,10 +1126,10 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     }
 }
 
-template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED, bool DELAYS, bool MASKED = false>
+template <int THREADS, int VPT, typename T, bool SOFT, bool RAGGED, bool DELAYS, bool MASKED = false, bool SHIFT = false>
 int launch_mma_bwd_fast_impl(const MmaParams& prm, cudaStream_t stream) {
     using L = FastLayout<THREADS * VPT, T, SOFT>;
-    auto kern = mma_bwd_fast_kernel<THREADS, VPT, T, SOFT, RAGGED, DELAYS, MASKED>;
+    auto kern = mma_bwd_fast_kernel<THREADS, VPT, T, SOFT, RAGGED, DELAYS, MASKED, SHIFT>;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -984,6 +1154,9 @@ int launch_mma_bwd_fast(const MmaParams& prm, cudaStream_t stream) {
     } else {
         // unmasked rows, TMA staging and 16-byte rows legal, every thread wholly inside or
         // outside the row
+        if (prm.shift && prm.S + 16 <= CAP && !(prm.flags & SIMULST_MMA_LEFT_PADDING) &&
+            (prm.mask == nullptr || (prm.flags & SIMULST_MMA_RIGHT_PADDING)))
+            return launch_mma_bwd_fast_impl<THREADS, VPT, T, SOFT, true, true, true, true>(prm, stream);
         if (!prm.vec_out || !prm.tma) return 1;
         if (prm.S > CAP || prm.S % VPT != 0) return 1;
         if (prm.mask != nullptr) {

@@ -39,6 +39,12 @@ struct MmaParams {
                             // 16-byte aligned superset of a row and the consumer reads at the row's offset in it
     int row_filter;         // masked calls only: 0 all rows, 1 only rows whose mask is a right-padding mask
                             // (j >= len), 2 only the other rows -- the two passes of a masked call
+    // Row pitches in ELEMENTS of each [N,T,S] tensor (the batch stride is T * pitch); S when dense.
+    int ld_p, ld_e, ld_alpha, ld_beta, ld_ga, ld_gb, ld_gp, ld_ge;
+    int shift;              // 1: dense kernels may take the row although its inputs are not 16-byte multiples
+                            // and / or S is not a multiple of the per-thread element count (SHIFT
+                            // instantiations: aligned-superset bulk copies, reads at the row's byte offset,
+                            // a live length per row); needs 16-byte pitched OUTPUT rows of >= roundup(S, VPT)
 };
 
 // Block-wide: is this row's padding mask of the form (j >= len), i.e. no live column after a
@@ -112,6 +118,88 @@ __device__ __forceinline__ void lds_row_shift(const T* __restrict__ row, int shi
         for (int k = 0; k < VPT; ++k) out[k] = to_f32<T>(row[shift + j0 + k]);
     }
 }
+
+// Dense SHIFT kernels: VPT consecutive elements of a staged row that starts `sh` BYTES into its ring
+// slot (sh = the row's global address & 15; a multiple of the element size), as float2 pairs.
+// The thread reads the ALIGNED 16-byte (8-byte when its span is not a 16-byte multiple) units that cover
+// its elements -- one unit more than an aligned row needs, conflict-free like the aligned read; word
+// loads at the shifted address would serialise 4- to 8-fold on the banks -- and realigns in registers
+// with selects on CTA-uniform conditions: by 8 bytes, by 4 bytes, and for 16-bit rows that start on an
+// odd element one byte permute per pair.  (A switch over the word shift that renames registers compiled
+// to ~40 instructions per row; this is ~16.)
+template <typename T, int VPT>
+__device__ __forceinline__ void lds_row2_sh(const void* __restrict__ slot, unsigned sh, int j0, int slot_bytes,
+                                            float2 (&out)[VPT / 2]) {
+    constexpr int B = VPT * (int)sizeof(T);             // bytes per thread: a multiple of 8
+    constexpr int U = (B % 16 == 0) ? 16 : 8;           // aligned unit
+    constexpr int NWORDS = B / 4 + U / 4;               // words fetched
+    // (clamped to the slot: only threads beyond the row's end can reach it, and everything they can see
+    //  there is neutral)
+    const int off = min(j0 * (int)sizeof(T) + (int)(sh & ~(unsigned)(U - 1)), slot_bytes - NWORDS * 4);
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(slot) + off;
+    unsigned w[NWORDS + 1];
+    if constexpr (U == 16) {
+#pragma unroll
+        for (int q = 0; q < NWORDS / 4; ++q) {
+            const uint4 t = *reinterpret_cast<const uint4*>(b + 16 * q);
+            w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < NWORDS / 2; ++q) {
+            const uint2 t = *reinterpret_cast<const uint2*>(b + 8 * q);
+            w[2 * q] = t.x; w[2 * q + 1] = t.y;
+        }
+    }
+    w[NWORDS] = 0u;
+    constexpr int NX = B / 4 + 1;                       // words that can matter after the whole-word shifts
+    if constexpr (U == 16) {
+        const bool by8 = (sh & 8u) != 0u;
+#pragma unroll
+        for (int i = 0; i < NX + 1; ++i) w[i] = by8 ? w[(i + 2 <= NWORDS) ? i + 2 : NWORDS] : w[i];
+    }
+    {
+        const bool by4 = (sh & 4u) != 0u;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) w[i] = by4 ? w[i + 1] : w[i];
+    }
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int q = 0; q < VPT / 2; ++q) out[q] = make_float2(__uint_as_float(w[2 * q]), __uint_as_float(w[2 * q + 1]));
+    } else {
+        const unsigned sel = (sh & 2u) ? 0x5432u : 0x3210u;
+#pragma unroll
+        for (int q = 0; q < VPT / 2; ++q) {
+            const unsigned v = __byte_perm(w[q], w[q + 1], sel);
+            if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                out[q] = make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+            } else {
+                out[q] = __half22float2(*reinterpret_cast<const __half2*>(&v));
+            }
+        }
+    }
+}
+// Element k (a run-time index, 0 <= k < VPT) of a register-resident pair array: a select tree on the bits
+// of k (VPT - 1 selects) instead of VPT compare + select pairs.
+template <int VPT>
+__device__ __forceinline__ float pick_el(const float2 (&a)[VPT / 2], int k) {
+    float v[VPT];
+#pragma unroll
+    for (int q = 0; q < VPT / 2; ++q) { v[2 * q] = a[q].x; v[2 * q + 1] = a[q].y; }
+#pragma unroll
+    for (int s = 1; s < VPT; s <<= 1) {
+        const bool hi = (k & s) != 0;
+#pragma unroll
+        for (int i = 0; i + s < VPT; i += 2 * s) v[i] = hi ? v[i + s] : v[i];
+    }
+    return v[0];
+}
+
+// byte offset of row `i` inside its aligned-superset copy: (base + i * pitch_bytes) & 15
+__device__ __forceinline__ unsigned sh_of(unsigned base_lo, int i, unsigned pitch_bytes) {
+    return (base_lo + (unsigned)i * pitch_bytes) & 15u;
+}
+__device__ __forceinline__ unsigned lo32(const void* p) { return (unsigned)reinterpret_cast<uintptr_t>(p); }
 
 // Global fp32 row access in float4 chunks when legal, scalar otherwise.
 template <int VPT, bool FULL = false>

@@ -46,10 +46,11 @@ __global__ void __launch_bounds__(THREADS) mma_fwd_kernel(const MmaParams prm, c
     const float fill = (prm.flags & SIMULST_MMA_ENERGY_F16_FILL) ? -1e4f : -1e8f;
     const bool vec_out = FULL || prm.vec_out != 0;
 
-    const T* gp = reinterpret_cast<const T*>(prm.p) + (size_t)n * T_len * S;
-    const T* ge = SOFT ? reinterpret_cast<const T*>(prm.e) + (size_t)n * T_len * S : nullptr;
-    float* g_alpha = prm.alpha + (size_t)n * T_len * S;
-    float* g_beta = SOFT ? prm.beta + (size_t)n * T_len * S : nullptr;
+    const int ld_p = prm.ld_p, ld_e = prm.ld_e, ld_a = prm.ld_alpha, ld_b = prm.ld_beta;     // row pitches (elements)
+    const T* gp = reinterpret_cast<const T*>(prm.p) + (size_t)n * T_len * ld_p;
+    const T* ge = SOFT ? reinterpret_cast<const T*>(prm.e) + (size_t)n * T_len * ld_e : nullptr;
+    float* g_alpha = prm.alpha + (size_t)n * T_len * ld_a;
+    float* g_beta = SOFT ? prm.beta + (size_t)n * T_len * ld_b : nullptr;
 
     Xchg xc(xraw);
 
@@ -100,26 +101,26 @@ __global__ void __launch_bounds__(THREADS) mma_fwd_kernel(const MmaParams prm, c
         if (prm.tma) {
             if (tid == 0) {
                 mbar_expect_tx(&bars[s], SOFT ? 2u * row_bytes : row_bytes);
-                tma_load_1d(stage_p(s), gp + (size_t)i * S, row_bytes, &bars[s]);
-                if (SOFT) tma_load_1d(stage_e(s), ge + (size_t)i * S, row_bytes, &bars[s]);
+                tma_load_1d(stage_p(s), gp + (size_t)i * ld_p, row_bytes, &bars[s]);
+                if (SOFT) tma_load_1d(stage_e(s), ge + (size_t)i * ld_e, row_bytes, &bars[s]);
             }
         } else if (prm.tma_shift) {
             if (tid == 0) {
                 unsigned np = 0u, ne = 0u;
-                const void* sp = tma_span(gp + (size_t)i * S, row_bytes, np);
-                const void* se = SOFT ? tma_span(ge + (size_t)i * S, row_bytes, ne) : nullptr;
+                const void* sp = tma_span(gp + (size_t)i * ld_p, row_bytes, np);
+                const void* se = SOFT ? tma_span(ge + (size_t)i * ld_e, row_bytes, ne) : nullptr;
                 mbar_expect_tx(&bars[s], np + ne);
                 tma_load_1d(stage_p(s), sp, np, &bars[s]);
                 if (SOFT) tma_load_1d(stage_e(s), se, ne, &bars[s]);
             }
         } else {
             T* dp = stage_p(s);
-            const T* sp = gp + (size_t)i * S;
+            const T* sp = gp + (size_t)i * ld_p;
 #pragma unroll 1
             for (int j = tid; j < S; j += THREADS) dp[j] = sp[j];
             if (SOFT) {
                 T* de = stage_e(s);
-                const T* se = ge + (size_t)i * S;
+                const T* se = ge + (size_t)i * ld_e;
 #pragma unroll 1
                 for (int j = tid; j < S; j += THREADS) de[j] = se[j];
             }
@@ -147,8 +148,8 @@ __global__ void __launch_bounds__(THREADS) mma_fwd_kernel(const MmaParams prm, c
 
         float p[VPT], E[VPT];
         if (prm.tma_shift) {
-            lds_row_shift<T, VPT>(stage_p(s), row_shift(gp + (size_t)i * S), j0, p);
-            if (SOFT) lds_row_shift<T, VPT>(stage_e(s), row_shift(ge + (size_t)i * S), j0, E);
+            lds_row_shift<T, VPT>(stage_p(s), row_shift(gp + (size_t)i * ld_p), j0, p);
+            if (SOFT) lds_row_shift<T, VPT>(stage_e(s), row_shift(ge + (size_t)i * ld_e), j0, E);
         } else {
             lds_row<T, VPT>(stage_p(s), j0, p);
             if (SOFT) lds_row<T, VPT>(stage_e(s), j0, E);
@@ -361,10 +362,10 @@ __global__ void __launch_bounds__(THREADS) mma_fwd_kernel(const MmaParams prm, c
                     const float v = is_live(k) ? ex[k] * R[k] : 0.f;
                     b[k] = fminf(fmaxf(v, 0.0f), 1.0f);
                 }
-                st_row_f32<VPT, FULL>(g_beta + (size_t)i * S, j0, S, vec_out, b);
+                st_row_f32<VPT, FULL>(g_beta + (size_t)i * ld_b, j0, S, vec_out, b);
             }
         }
-        st_row_f32<VPT, FULL>(g_alpha + (size_t)i * S, j0, S, vec_out, a);
+        st_row_f32<VPT, FULL>(g_alpha + (size_t)i * ld_a, j0, S, vec_out, a);
     }
 
     // ---- data-error reporting (prob_check / safe_cumprod semantics), slow path only on error
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(THREADS) mma_fwd_kernel(const MmaParams prm, c
             for (int i = 0; i < T_len; ++i)
                 for (int k = 0; k < VPT; ++k)
                     if (j0 + k < S) {
-                        const float v = to_f32<T>(gp[(size_t)i * S + j0 + k]);
+                        const float v = to_f32<T>(gp[(size_t)i * ld_p + j0 + k]);
                         bits |= prob_bits(v);
                         if ((1.0f - v) + eps < 0.f) bits |= SIMULST_ST_NEGPROD;
                     }

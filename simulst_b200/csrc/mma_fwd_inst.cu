@@ -21,7 +21,7 @@ int INST_NAME(const MmaParams& prm, int mode, int threads, int vpt, cudaStream_t
 #define X(TH, VP)                                                                         \
     if (threads == TH && vpt == VP) {                                                     \
         if constexpr (TH <= kPipeMaxThreads) {                                            \
-            if (prm.tma && prm.pipe && mode != kModeSoftCk) {                             \
+            if ((prm.tma || prm.shift) && prm.pipe && mode != kModeSoftCk) {              \
                 const int rc = mode == kModeHard ? launch_mma_fwd_pipe<TH, VP, InstT, false>(prm, stream) \
                                                  : launch_mma_fwd_pipe<TH, VP, InstT, true>(prm, stream); \
                 if (rc != 1) return rc;         /* 1 = row too long for the pipelined kernel */ \

@@ -75,11 +75,24 @@ struct PipeStatic {
 // outside the row; outside threads initialise the ring tails to neutral values once (p = 0,
 // energy = -inf; the bulk copies only write [0, S)), compute without bounds checks, skip stores.
 // MASKED (with FULL and RAGGED): padding_mask is a RIGHT-padding mask (caller's promise,
-// SIMULST_MMA_RIGHT_PADDING): row n is live on [0, L_n); columns >= L_n are neutralised after
-// each load (p = 0, energy = -inf) by a test that is thread-uniform except in the one thread
-// the boundary falls into; alpha and beta come out zero there, and mass preservation ADDS its
-// residual at L_n - 1 (monotonic_attention.py:186-193).
-template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS, bool RAGGED = false, bool MASKED = false>
+// SIMULST_MMA_RIGHT_PADDING): row n is live on [0, L_n).  Only the LIVE bytes of a row are copied
+// (rounded up to the 16-byte granule), every ring slot beyond them is initialised once to neutral
+// values (p = 0, energy = -inf), and the thread that owns column L_n - 1 (the "fixer") overwrites the
+// few columns of copy overhang behind the row's end with neutral values one step before the row is
+// used -- so the step loop reads every row without per-element tests (the earlier version masked in
+// registers under divergent branches: the warp the boundary falls into ran ~100 extra instructions
+// per step and every other warp waited for it at the barrier, +28 % at the training shape).  alpha
+// and beta come out zero beyond L_n, and mass preservation ADDS its residual at L_n - 1
+// (monotonic_attention.py:186-193).
+// SHIFT (with FULL, RAGGED and MASKED): rows of the INPUT tensors need not be 16-byte multiples and S
+// need not be a multiple of VPT.  Every row is fetched as its 16-byte aligned superset and read at its
+// byte offset inside the staged copy (lds_row2_sh); the live length is min(S, mask length) -- the mask
+// is optional, without one the reference's no-mask rule applies (column S-1 REPLACED) -- and the
+// thread the row ends in neutralises its columns beyond it like a masked row's boundary thread.
+// The OUTPUT rows must be 16-byte pitched with room for whole threads (pitch >= roundup(S, VPT)):
+// the padding columns receive zeros.  The CTA must have 16 spare columns (S + 16 <= THREADS*VPT).
+template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS, bool RAGGED = false, bool MASKED = false,
+          bool SHIFT = false>
 __global__ void __launch_bounds__(THREADS, (THREADS * VPT <= 1024 ? 4 : (THREADS <= 160 ? 3 : (THREADS <= 256 ? 2 : 1))))
 mma_fwd_pipe_kernel(const MmaParams prm) {
     using PS = PipeStatic<THREADS, VPT, T, SOFT>;
@@ -106,10 +119,15 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
     const bool vec_out = FULL || prm.vec_out != 0;
     constexpr int NS = PS::kNS;
 
-    const T* gp = reinterpret_cast<const T*>(prm.p) + (size_t)n * T_len * S;
-    const T* ge = SOFT ? reinterpret_cast<const T*>(prm.e) + (size_t)n * T_len * S : nullptr;
-    float* g_alpha = prm.alpha + (size_t)n * T_len * S;
-    float* g_beta = SOFT ? prm.beta + (size_t)n * T_len * S : nullptr;
+    const int ld_p = prm.ld_p, ld_e = prm.ld_e, ld_a = prm.ld_alpha, ld_b = prm.ld_beta;
+    const T* gp = reinterpret_cast<const T*>(prm.p) + (size_t)n * T_len * ld_p;
+    const T* ge = SOFT ? reinterpret_cast<const T*>(prm.e) + (size_t)n * T_len * ld_e : nullptr;
+    float* g_alpha = prm.alpha + (size_t)n * T_len * ld_a;
+    float* g_beta = SOFT ? prm.beta + (size_t)n * T_len * ld_b : nullptr;
+    // SHIFT: byte offset of a row inside its staged aligned superset, from the low address bits
+    const unsigned p_lo = lo32(gp), e_lo = lo32(ge);
+    const unsigned p_pitch = (unsigned)ld_p * (unsigned)sizeof(T), e_pitch = (unsigned)ld_e * (unsigned)sizeof(T);
+    (void)p_lo; (void)e_lo; (void)p_pitch; (void)e_pitch;
 
     // ---- per-row constants: validity bits, padding mask, column rewritten by mass preservation
     unsigned in_bits = 0u, live_bits = 0u;
@@ -131,11 +149,17 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
     // other columns; right padding -> ADD the residual of all columns at src_len-1.
     if constexpr (FULL && MASKED) {
         if (j0 < S) {
-            const uint8_t* mrow = prm.mask + (size_t)n * S + j0;
+            if (SHIFT && prm.mask == nullptr) {
+                n_live = min(VPT, S - j0);
+            } else {
+                const uint8_t* mrow = prm.mask + (size_t)n * S + j0;
 #pragma unroll
-            for (int k = 0; k < VPT; ++k) n_live += (mrow[k] == 0) ? 1 : 0;
+                for (int k = 0; k < VPT; ++k)
+                    if (!SHIFT || j0 + k < S) n_live += (mrow[k] == 0) ? 1 : 0;
+            }
         }
     }
+    const bool count_live = (!FULL || MASKED) && (prm.mask != nullptr || SHIFT);
     const bool mp_add = (!FULL || MASKED) && prm.mask != nullptr && !(prm.flags & SIMULST_MMA_LEFT_PADDING);
     int last = S - 1;
 
@@ -144,7 +168,7 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
         mbar_fence_init();
     }
     const bool inside = !RAGGED || j0 < S;
-    if (RAGGED && !inside) {
+    if (RAGGED && !MASKED && !inside) {
         const T ninf = from_f32<T>(-INFINITY), zero = from_f32<T>(0.f);
         for (int s = 0; s < NS; ++s) {
             T* sp = reinterpret_cast<T*>(stage0 + (s * PS::kRows) * PS::kRowBytes);
@@ -156,12 +180,12 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
             }
         }
     }
-    if (mp_add) {
+    if (SHIFT ? count_live : mp_add) {
         const float cnt = warp_sum((float)n_live);
         if (lane == 0) xbuf[warp] = cnt;
     }
     __syncthreads();
-    if (mp_add) {
+    if (SHIFT ? count_live : mp_add) {
         last = (int)combine_sum<NW>(xbuf, lane) - 1;
         __syncthreads();
     }
@@ -169,23 +193,58 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
     // live columns of this thread (right-padded rows); VPT everywhere else
     const int nl = MASKED ? max(0, min(VPT, last + 1 - j0)) : VPT;
     (void)nl;
+    const int L_row = last + 1;                                     // MASKED: live length of the row
+    const bool fixer = MASKED && last >= j0 && last < j0 + VPT;     // owner of the last live column
+    (void)L_row; (void)fixer;
+    if constexpr (FULL && MASKED) {
+        if (nl < VPT) {
+            // neutral ring slots from this thread's columns on (the copies rewrite the live bytes)
+            const T ninf = from_f32<T>(-INFINITY), zero = from_f32<T>(0.f);
+            for (int s = 0; s < PS::kNS; ++s) {
+                T* sp = reinterpret_cast<T*>(stage0 + (s * PS::kRows) * PS::kRowBytes);
+                T* se = reinterpret_cast<T*>(stage0 + (s * PS::kRows + 1) * PS::kRowBytes);
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) {
+                    sp[j0 + k] = zero;
+                    if (SOFT) se[j0 + k] = ninf;
+                }
+            }
+            fence_proxy_async();
+        }
+    }
     if constexpr (FULL && MASKED) {
         // the promise is checked, not trusted: a row whose mask is not (j >= len) flags the status
         // word AND has its outputs poisoned with NaN, so a broken promise cannot train on silently
         // even when nobody reads the (lazily inspected) status word
         bool ok = true;
-        if (j0 < S) {
+        if (j0 < S && !(SHIFT && prm.mask == nullptr)) {
             const uint8_t* mrow = prm.mask + (size_t)n * S + j0;
 #pragma unroll
-            for (int k = 0; k < VPT; ++k) ok = ok && ((mrow[k] == 0) == (k < nl));
+            for (int k = 0; k < VPT; ++k)
+                if (!SHIFT || j0 + k < S) ok = ok && ((mrow[k] == 0) == (k < nl));
         }
         if (__syncthreads_or(ok ? 0 : 1)) {
             if (tid == 0 && prm.status != nullptr) atomicOr(prm.status, SIMULST_ST_NOT_RIGHT_PADDED);
             const float qnan = __int_as_float(0x7fc00000);
-            for (size_t q = tid; q < (size_t)T_len * S; q += THREADS) {
-                g_alpha[q] = qnan;
-                if (SOFT) g_beta[q] = qnan;
-            }
+            for (int i = 0; i < T_len; ++i)
+                for (int j = tid; j < S; j += THREADS) {
+                    g_alpha[(size_t)i * ld_a + j] = qnan;
+                    if (SOFT) g_beta[(size_t)i * ld_b + j] = qnan;
+                }
+            return;
+        }
+    }
+    if constexpr (FULL && MASKED) {
+        if (last < 0) {
+            // no live column: alpha = beta = 0 for the whole row (no mass-preservation column exists)
+            float2 z2[H];
+#pragma unroll
+            for (int q = 0; q < H; ++q) z2[q] = f2(0.f);
+            if (inside)
+                for (int i = 0; i < T_len; ++i) {
+                    st_row2_f32<VPT, FULL>(g_alpha + (size_t)i * ld_a, j0, S, vec_out, z2);
+                    if (SOFT) st_row2_f32<VPT, FULL>(g_beta + (size_t)i * ld_b, j0, S, vec_out, z2);
+                }
             return;
         }
     }
@@ -199,7 +258,7 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
     auto at_last = [&](int k) -> bool { return ((FULL && !MASKED) ? k == VPT - 1 : true) && k == k_last; };
 
     // ---- row staging ring
-    const unsigned row_bytes = (unsigned)(S * sizeof(T));
+    const unsigned row_bytes = (unsigned)((MASKED ? L_row : S) * sizeof(T));
     auto stage_p = [&](int s) { return reinterpret_cast<T*>(stage0 + (s * PS::kRows) * PS::kRowBytes); };
     auto stage_e = [&](int s) { return reinterpret_cast<T*>(stage0 + (s * PS::kRows + 1) * PS::kRowBytes); };
     // one elected lane of warp 0 copies the p row, one of warp 1 (if there is one) the energy
@@ -207,17 +266,62 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
     auto issue = [&](int i, int s) {
         if (warp == 0) {
             if (elect_one()) {
-                mbar_expect_tx(&bars[s], (SOFT && kIssuers == 1) ? 2u * row_bytes : row_bytes);
-                tma_load_1d(stage_p(s), gp + (size_t)i * S, row_bytes, &bars[s]);
-                if (SOFT && kIssuers == 1) tma_load_1d(stage_e(s), ge + (size_t)i * S, row_bytes, &bars[s]);
+                if constexpr (MASKED) {
+                    unsigned np = 0u, ne = 0u;
+                    const void* sp = tma_span(gp + (size_t)i * ld_p, row_bytes, np);
+                    const void* se = (SOFT && kIssuers == 1) ? tma_span(ge + (size_t)i * ld_e, row_bytes, ne) : nullptr;
+                    mbar_expect_tx(&bars[s], np + ne);
+                    tma_load_1d(stage_p(s), sp, np, &bars[s]);
+                    if (SOFT && kIssuers == 1) tma_load_1d(stage_e(s), se, ne, &bars[s]);
+                } else {
+                    mbar_expect_tx(&bars[s], (SOFT && kIssuers == 1) ? 2u * row_bytes : row_bytes);
+                    tma_load_1d(stage_p(s), gp + (size_t)i * ld_p, row_bytes, &bars[s]);
+                    if (SOFT && kIssuers == 1) tma_load_1d(stage_e(s), ge + (size_t)i * ld_e, row_bytes, &bars[s]);
+                }
             }
         } else if (SOFT && kIssuers == 2 && warp == 1) {
             if (elect_one()) {
-                mbar_expect_tx(&bars[s], row_bytes);
-                tma_load_1d(stage_e(s), ge + (size_t)i * S, row_bytes, &bars[s]);
+                if constexpr (MASKED) {
+                    unsigned ne = 0u;
+                    const void* se = tma_span(ge + (size_t)i * ld_e, row_bytes, ne);
+                    mbar_expect_tx(&bars[s], ne);
+                    tma_load_1d(stage_e(s), se, ne, &bars[s]);
+                } else {
+                    mbar_expect_tx(&bars[s], row_bytes);
+                    tma_load_1d(stage_e(s), ge + (size_t)i * ld_e, row_bytes, &bars[s]);
+                }
             }
         }
     };
+    // SHIFT: staged row -> float2 pairs; reads are clamped to the slot (threads beyond the row read
+    // neutral bytes wherever they land)
+    auto load_sh = [&](const T* slot, unsigned sh, float2 (&v)[H]) {
+        if (sh == 0u) {                     // CTA-uniform: this row happens to be aligned
+            unsigned dummy = 0u;
+            lds_row2<T, VPT, false>(slot + j0, v, dummy);
+        } else {
+            lds_row2_sh<T, VPT>(slot, sh, j0, THREADS * VPT * (int)sizeof(T), v);
+        }
+    };
+    // MASKED: the fixer neutralises the copy overhang [L, end of the last 16-byte granule) of a landed row
+    auto fix_row = [&](T* slot, unsigned sh, float fillv) {
+        const unsigned live_end = sh + (unsigned)L_row * (unsigned)sizeof(T);
+        const unsigned dirt_end = (live_end + 15u) & ~15u;
+        unsigned char* b = reinterpret_cast<unsigned char*>(slot);
+        const T nv = from_f32<T>(fillv);
+        for (unsigned o = live_end; o < dirt_end; o += (unsigned)sizeof(T)) *reinterpret_cast<T*>(b + o) = nv;
+        if constexpr (SHIFT) {
+            // the previous row in this slot may have started up to 15 bytes later and reached one granule further
+            if (dirt_end + 16u <= (unsigned)(THREADS * VPT * sizeof(T))) {
+                Pack<T, 16 / (int)sizeof(T)> pk;
+#pragma unroll
+                for (int k = 0; k < 16 / (int)sizeof(T); ++k) pk.v[k] = nv;
+                *reinterpret_cast<Pack<T, 16 / (int)sizeof(T)>*>(b + dirt_end) = pk;
+            }
+        }
+    };
+    const float eps_x = (MASKED && nl == 0) ? 0.f : eps;    // no eps from the columns of a thread beyond the row
+    unsigned umax32 = 0u;                   // SHIFT: first-level prob_check on the fp32 bit patterns
     for (int i = 0; i < NS && i < T_len; ++i) issue(i, i);
 
     const float one_eps = 1.0f + eps;       // first element of the exclusive cumprod (functions.py:28-33)
@@ -264,13 +368,16 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
             unsigned parM = parI;
             if (slotM == NS) { slotM = 0; parM ^= 1u; }
             mbar_wait(&bars[slotM], parM);
-            if (MASKED && nl < VPT) {
+            if (MASKED && fixer) {
+                fix_row(stage_p(slotM), SHIFT ? sh_of(p_lo, it + 2, p_pitch) : 0u, 0.f);
+                fix_row(stage_e(slotM), SHIFT ? sh_of(e_lo, it + 2, e_pitch) : 0u, -INFINITY);
+            }
+            if constexpr (SHIFT) {
                 float2 Em[H];
-                unsigned dummy = 0u;
-                lds_row2<T, VPT, false>(stage_e(slotM) + j0, Em, dummy);
+                load_sh(stage_e(slotM), sh_of(e_lo, it + 2, e_pitch), Em);
+                em = fmaxf(Em[0].x, Em[0].y);
 #pragma unroll
-                for (int k = 0; k < VPT; ++k)
-                    if (k < nl) em = fmaxf(em, SIMULST_EL(Em, k));
+                for (int q = 1; q < H; ++q) em = fmaxf(em, fmaxf(Em[q].x, Em[q].y));
             } else if constexpr (FULL && sizeof(T) == 2 && VPT % 8 == 0) {
                 // packed 16-bit max, one conversion at the end
                 using T2 = typename std::conditional<std::is_same<T, __half>::value, __half2, __nv_bfloat162>::type;
@@ -299,24 +406,36 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
                 for (int q = 1; q < H; ++q) em = fmaxf(em, fmaxf(Em[q].x, Em[q].y));
             }
         }
+        if (MASKED && nl == 0) em = -INFINITY;      // a thread beyond the row may have read overhang not yet fixed
+        if (MASKED && !SOFT && fixer && (STEADY || it + 2 < T_len)) {
+            // hard attention has no MAXS stage: the fixer alone looks two rows ahead
+            int slotM = slotI + 1;
+            unsigned parM = parI;
+            if (slotM == NS) { slotM = 0; parM ^= 1u; }
+            mbar_wait(&bars[slotM], parM);
+            fix_row(stage_p(slotM), SHIFT ? sh_of(p_lo, it + 2, p_pitch) : 0u, 0.f);
+        }
         // ---- INV(it+1): local chains
         float2 p_n[H], cpre[H], Dl[H];
         float xinc = 1.f, einc = 0.f;
         if (doI) {
             if (!SOFT) mbar_wait(&bars[slotI], parI);      // with SOFT, MAXS waited for this row one iteration ago
-            lds_row2<T, VPT, FULL>(stage_p(slotI) + j0, p_n, umax);
             float2 E_n[H];
-            if (SOFT) {
-                unsigned dummy = 0u;
-                lds_row2<T, VPT, false>(stage_e(slotI) + j0, E_n, dummy);
+            if constexpr (SHIFT) {
+                load_sh(stage_p(slotI), sh_of(p_lo, it + 1, p_pitch), p_n);
+                if (SOFT) load_sh(stage_e(slotI), sh_of(e_lo, it + 1, e_pitch), E_n);
+            } else {
+                lds_row2<T, VPT, FULL>(stage_p(slotI) + j0, p_n, umax);
+                if (SOFT) {
+                    unsigned dummy = 0u;
+                    lds_row2<T, VPT, false>(stage_e(slotI) + j0, E_n, dummy);
+                }
             }
-            if (MASKED && nl < VPT) {
+            if constexpr (SHIFT) {
+                // a valid probability has the bit pattern of a float in [+0, 1]: unsigned compare
 #pragma unroll
-                for (int k = 0; k < VPT; ++k)
-                    if (k >= nl) {
-                        SIMULST_EL(p_n, k) = 0.f;
-                        if (SOFT) SIMULST_EL(E_n, k) = -INFINITY;
-                    }
+                for (int q = 0; q < H; ++q)
+                    umax32 = max(umax32, max(__float_as_uint(p_n[q].x), __float_as_uint(p_n[q].y)));
             }
             if constexpr (!FULL) {
 #pragma unroll
@@ -332,7 +451,7 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
             xinc = local_cumprod<VPT>(p_n, eps, cpre);
             if (SOFT) {
                 float2 unused[H], ex_n[H];
-                einc = local_exp_prefix<VPT, false>(E_n, m_cur, eps, unused, ex_n, Dl);
+                einc = local_exp_prefix<VPT, false>(E_n, m_cur, eps_x, unused, ex_n, Dl);
                 nan_out = nan_out || (einc != einc);
 #pragma unroll
                 for (int q = 0; q < VPT / 4; ++q)
@@ -410,12 +529,12 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
                     for (int k = 0; k < VPT; ++k)
                         if (!is_live(k)) SIMULST_EL(b, k) = 0.f;
                 }
-                if (MASKED && nl < VPT) {
-#pragma unroll
-                    for (int k = 0; k < VPT; ++k)
-                        if (k >= nl) SIMULST_EL(b, k) = 0.f;
+                if (inside) st_row2_f32<VPT, FULL>(g_beta + (size_t)i * ld_b, j0, S, vec_out, b);
+                if (MASKED && nl > 0 && nl < VPT) {
+                    // the thread the row ends in: its columns beyond the row hold eps * R, not zero (threads
+                    // wholly beyond the row compute exact zeros: their eps is zero) -- overwrite them
+                    for (int k = nl; k < VPT; ++k) g_beta[(size_t)i * ld_b + j0 + k] = 0.f;
                 }
-                if (inside) st_row2_f32<VPT, FULL>(g_beta + (size_t)i * S, j0, S, vec_out, b);
             }
             if (want_d) {
                 // expected delay (mma_criterion.py:146-157): the weighted row sum left out the
@@ -426,7 +545,7 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
             }
             if (own_last) {
                 // the row itself was stored one iteration ago; patch the one column
-                g_alpha[(size_t)i * S + last] = mp_add ? (a_last_raw + resid) : resid;
+                g_alpha[(size_t)i * ld_a + last] = mp_add ? (a_last_raw + resid) : resid;
                 if (prm.side != nullptr)
                     *reinterpret_cast<float2*>(prm.side + ((size_t)n * T_len + i) * 2) = make_float2(a_last_raw, row_total);
             }
@@ -438,14 +557,21 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
             finish_u_prefix<VPT>(ubase, sl, P, sfull, z);
 #pragma unroll
             for (int q = 0; q < H; ++q) a_prev[q] = min2(z[q], 1.0f);      // z >= 0: P >= 0, s >= 0
-            if (inside) st_row2_f32<VPT, FULL>(g_alpha + (size_t)it * S, j0, S, vec_out, a_prev);
+            if (inside) st_row2_f32<VPT, FULL>(g_alpha + (size_t)it * ld_a, j0, S, vec_out, a_prev);
             if (mp || SOFT || want_d) {
                 // alpha entering the row sum / the soft-attention numerator: the mass-preservation
                 // column is left out when it is REPLACED (its residual is added analytically)
                 float2 a_s[H];
 #pragma unroll
                 for (int q = 0; q < H; ++q) a_s[q] = a_prev[q];
-                if (own_last) {
+                if constexpr (MASKED) {
+                    if (own_last) a_last_raw = pick_el<VPT>(a_s, k_last);
+                    if (!mp_add) {              // CTA-uniform: the no-mask rule on a SHIFT row (column REPLACED)
+#pragma unroll
+                        for (int k = 0; k < VPT; ++k)
+                            if (own_last && k == k_last) SIMULST_EL(a_s, k) = 0.f;
+                    }
+                } else if (own_last) {
 #pragma unroll
                     for (int k = 0; k < VPT; ++k)
                         if (at_last(k)) {
@@ -478,7 +604,9 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
             if (SOFT) {
                 const float ebase = xw_prefix_add<NW>(xw + 2 * kXStride, warp, lane) + eexc;
                 finish_exp_prefix<VPT>(ebase, eps, Dl, rD);
-                if (own_last) {
+                if constexpr (MASKED) {
+                    if (own_last) bcast[(it + 1) & 3] = pick_el<VPT>(rD, k_last);
+                } else if (own_last) {
 #pragma unroll
                     for (int k = 0; k < VPT; ++k)
                         if (at_last(k)) bcast[(it + 1) & 3] = SIMULST_EL(rD, k);
@@ -499,13 +627,13 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
     // ---- data-error reporting (prob_check / safe_cumprod semantics), slow path only on error
     if (prm.status != nullptr) {
         if (nan_out) atomicOr(prm.status, SIMULST_ST_NAN);
-        if (FULL) bad = umax_trips<T>(umax);
+        if (FULL) bad = SHIFT ? (umax32 > 0x3f800000u) : umax_trips<T>(umax);
         if (bad) {
             unsigned bits = 0u;
             for (int i = 0; i < T_len; ++i)
                 for (int k = 0; k < VPT; ++k)
                     if (j0 + k < S) {
-                        const float v = to_f32<T>(gp[(size_t)i * S + j0 + k]);
+                        const float v = to_f32<T>(gp[(size_t)i * ld_p + j0 + k]);
                         bits |= prob_bits(v);
                         if ((1.0f - v) + eps < 0.f) bits |= SIMULST_ST_NEGPROD;
                     }
@@ -516,11 +644,13 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
 
 // ------------------------------------------------------------------ host-side launcher
 // Returns 1 when the row does not fit the pipelined kernel (caller falls back to the generic one).
-template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS, bool RAGGED = false, bool MASKED = false>
+template <int THREADS, int VPT, typename T, bool SOFT, bool FULL, bool DELAYS, bool RAGGED = false, bool MASKED = false,
+          bool SHIFT = false>
 int launch_mma_fwd_pipe_impl(const MmaParams& prm, cudaStream_t stream) {
     using PS = PipeStatic<THREADS, VPT, T, SOFT>;
     if (!PS::kFits) return 1;
-    auto kern = mma_fwd_pipe_kernel<THREADS, VPT, T, SOFT, FULL, DELAYS, RAGGED, MASKED>;
+    if (MASKED && PS::kNS < 2) return 1;        // the fixer looks two rows ahead
+    auto kern = mma_fwd_pipe_kernel<THREADS, VPT, T, SOFT, FULL, DELAYS, RAGGED, MASKED, SHIFT>;
     static size_t attr_set[64] = {};    // per device: largest dynamic smem size opted into
     int dev = 0;
     cudaGetDevice(&dev);
@@ -538,6 +668,12 @@ int launch_mma_fwd_pipe_impl(const MmaParams& prm, cudaStream_t stream) {
 // SOFT here means infinite lookback; requires prm.tma (16-byte aligned rows).
 template <int THREADS, int VPT, typename T, bool SOFT>
 int launch_mma_fwd_pipe(const MmaParams& prm, cudaStream_t stream) {
+    // rows that are not 16-byte multiples / do not divide among the threads: shifted staging, live length
+    // min(S, mask length); a mask needs the right-padding promise like the aligned masked kernel
+    if (prm.shift && prm.S + 16 <= THREADS * VPT && !(prm.flags & SIMULST_MMA_LEFT_PADDING) &&
+        (prm.mask == nullptr || (prm.flags & SIMULST_MMA_RIGHT_PADDING)))
+        return launch_mma_fwd_pipe_impl<THREADS, VPT, T, SOFT, true, true, true, true, true>(prm, stream);
+    if (!prm.tma) return 1;
     // right-padded rows (caller's promise): dense path with a per-row live length
     if (prm.mask != nullptr && (prm.flags & SIMULST_MMA_RIGHT_PADDING) && !(prm.flags & SIMULST_MMA_LEFT_PADDING) &&
         prm.vec_out && prm.S % VPT == 0 && prm.S <= THREADS * VPT)

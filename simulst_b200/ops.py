@@ -22,6 +22,25 @@ def _mask_u8(mask: Optional[Tensor], n: int, s: int, device) -> Optional[Tensor]
     return (m != 0).contiguous().view(torch.uint8)
 
 
+def _rows(x: Tensor):
+    """A [N,T,S] tensor as (tensor, row pitch in elements) for the pitched entry points: dense tensors and
+    tensors whose rows are unit-stride with a uniform pitch (e.g. x_padded[..., :S]) pass as they are,
+    anything else is made contiguous first."""
+    n, t, s = x.shape
+    if x.is_contiguous():
+        return x, s
+    if x.stride(2) == 1 and x.stride(1) >= s and x.stride(0) == t * x.stride(1):
+        return x, x.stride(1)
+    return x.contiguous(), s
+
+
+def _empty_rows(n: int, t: int, s: int, ld: int, dtype, dev):
+    """[N,T,S] output with row pitch ld: the [..., :S] view of a [N,T,ld] buffer when ld > S."""
+    if ld == s:
+        return torch.empty((n, t, s), dtype=dtype, device=dev)
+    return torch.empty((n, t, ld), dtype=dtype, device=dev)[..., :s]
+
+
 class MMATrainFunction(torch.autograd.Function):
     """(p_choose, soft_energy) -> (alpha, beta): steps 2-3 of
     MonotonicAttention.monotonic_attention_process_train
@@ -40,19 +59,22 @@ class MMATrainFunction(torch.autograd.Function):
         if s > _lib.MMA_MAX_SRC:
             raise ValueError(f"src_len {s} exceeds the on-chip row limit {_lib.MMA_MAX_SRC}")
         soft = soft_energy is not None
-        p = p_choose.contiguous()
-        e = None
+        p, e = p_choose, None
         flags = 0
         if soft:
             if tuple(soft_energy.shape) != (n, t, s):
                 raise ValueError("soft_energy must have the shape of p_choose")
             if soft_energy.dtype == torch.float16:
                 flags |= _lib.MMA_ENERGY_F16_FILL      # -1e4 fill, monotonic_attention.py:106
-            e = soft_energy.contiguous()
+            e = soft_energy
             if e.dtype != p.dtype:                      # kernel wants one activation dtype
                 common = torch.promote_types(e.dtype, p.dtype)
                 e, p = e.to(common), p.to(common)
             flags |= _lib.MMA_SOFT
+            e, ld_e = _rows(e)
+        else:
+            ld_e = 0
+        p, ld_p = _rows(p)
         if mass_preservation:
             flags |= _lib.MMA_MASS_PRESERVATION
         if left_padding:
@@ -60,8 +82,10 @@ class MMATrainFunction(torch.autograd.Function):
         mask = _mask_u8(padding_mask, n, s, dev)
         if mask is not None and not left_padding and _lib.right_padding_assumed():
             flags |= _lib.MMA_RIGHT_PADDING
-        alpha = torch.empty((n, t, s), dtype=torch.float32, device=dev)
-        beta = torch.empty((n, t, s), dtype=torch.float32, device=dev) if soft else None
+        # rows that are not 16-byte multiples: 16-byte pitched outputs keep them on the dense kernels
+        ld_out = int(lib.simulst_mma_out_pitch(s)) if _lib.pitched_outputs() else s
+        alpha = _empty_rows(n, t, s, ld_out, torch.float32, dev)
+        beta = _empty_rows(n, t, s, ld_out, torch.float32, dev) if soft else None
         # a row whose mask leaves no live column has no mass-preservation column: the kernels
         # write nothing for it, so with a mask these two small buffers start as zeros
         small = torch.zeros if mask is not None else torch.empty
@@ -70,15 +94,16 @@ class MMATrainFunction(torch.autograd.Function):
         status = _lib.status_word(dev)
         chunk = int(chunk_size) if chunk_size else 0
         with torch.cuda.device(dev):
-            rc = lib.simulst_mma_train_fwd_delays(
-                _lib.ptr(p), _lib.dtype_enum(p.dtype), _lib.ptr(e),
-                _lib.dtype_enum(e.dtype) if soft else 0, _lib.ptr(mask),
-                _lib.ptr(alpha), _lib.ptr(beta), _lib.ptr(side), _lib.ptr(delays),
+            rc = lib.simulst_mma_train_fwd_pitched(
+                _lib.ptr(p), _lib.dtype_enum(p.dtype), ld_p, _lib.ptr(e),
+                _lib.dtype_enum(e.dtype) if soft else 0, ld_e, _lib.ptr(mask),
+                _lib.ptr(alpha), ld_out, _lib.ptr(beta), ld_out, _lib.ptr(side), _lib.ptr(delays),
                 n, t, s, float(eps), chunk, flags, _lib.ptr(status), _lib.stream_ptr(dev))
-        _lib.check(rc, "simulst_mma_train_fwd_delays")
+        _lib.check(rc, "simulst_mma_train_fwd_pitched")
         _lib.maybe_check(dev)
         ctx.save_for_backward(p, e, mask, alpha, side)
         ctx.cfg = (n, t, s, float(eps), chunk, flags, soft)
+        ctx.pitches = (ld_p, ld_e, ld_out)
         ctx.in_dtypes = (p_choose.dtype, soft_energy.dtype if soft else None)
         ctx.mark_non_differentiable()
         ctx.set_materialize_grads(False)        # an unused output costs no zero-filled gradient
@@ -91,20 +116,21 @@ class MMATrainFunction(torch.autograd.Function):
         p, e, mask, alpha, side = ctx.saved_tensors
         n, t, s, eps, chunk, flags, soft = ctx.cfg
         dev = p.device
-        ga = g_alpha.contiguous().float() if g_alpha is not None else None
-        gb = g_beta.contiguous().float() if (soft and g_beta is not None) else None
+        ld_p, ld_e, ld_out = ctx.pitches
+        ga, ld_ga = _rows(g_alpha.float()) if g_alpha is not None else (None, 0)
+        gb, ld_gb = _rows(g_beta.float()) if (soft and g_beta is not None) else (None, 0)
         gd = g_delays.contiguous().float() if (g_delays is not None and g_delays.numel() == n * t) else None
-        grad_p = torch.empty_like(p)
-        grad_e = torch.empty_like(e) if soft else None
+        grad_p = _empty_rows(n, t, s, ld_out, p.dtype, dev)
+        grad_e = _empty_rows(n, t, s, ld_out, e.dtype, dev) if soft else None
         with torch.cuda.device(dev):
-            rc = lib.simulst_mma_train_bwd_delays(
-                _lib.ptr(p), _lib.dtype_enum(p.dtype), _lib.ptr(e),
-                _lib.dtype_enum(e.dtype) if soft else 0, _lib.ptr(mask),
-                _lib.ptr(alpha), _lib.ptr(side), _lib.ptr(ga), _lib.ptr(gb), _lib.ptr(gd),
-                _lib.ptr(grad_p), _lib.dtype_enum(p.dtype), _lib.ptr(grad_e),
-                _lib.dtype_enum(e.dtype) if soft else 0,
+            rc = lib.simulst_mma_train_bwd_pitched(
+                _lib.ptr(p), _lib.dtype_enum(p.dtype), ld_p, _lib.ptr(e),
+                _lib.dtype_enum(e.dtype) if soft else 0, ld_e, _lib.ptr(mask),
+                _lib.ptr(alpha), ld_out, _lib.ptr(side), _lib.ptr(ga), ld_ga, _lib.ptr(gb), ld_gb, _lib.ptr(gd),
+                _lib.ptr(grad_p), _lib.dtype_enum(p.dtype), ld_out, _lib.ptr(grad_e),
+                _lib.dtype_enum(e.dtype) if soft else 0, ld_out,
                 n, t, s, eps, chunk, flags, _lib.stream_ptr(dev))
-        _lib.check(rc, "simulst_mma_train_bwd_delays")
+        _lib.check(rc, "simulst_mma_train_bwd_pitched")
         p_dt, e_dt = ctx.in_dtypes
         if grad_p.dtype != p_dt:
             grad_p = grad_p.to(p_dt)

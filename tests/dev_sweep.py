@@ -36,28 +36,32 @@ def mma_point(N, T, S):
     dt = torch.bfloat16
     p = torch.sigmoid(torch.randn(N, T, S, generator=g) - 2).to(dev, dt)
     e = torch.randn(N, T, S, generator=g).to(dev, dt)
-    alpha = torch.empty(N, T, S, device=dev); beta = torch.empty_like(alpha)
+    # inputs dense (what a caller hands over); outputs with the pitch the library asks for (= S whenever
+    # dense rows are already 16-byte multiples), as the Python wrapper allocates them
+    ld = S if os.environ.get("DENSE_OUT") else int(lib.simulst_mma_out_pitch(S))
+    alpha = torch.empty(N, T, ld, device=dev); beta = torch.empty_like(alpha)
     side = torch.empty(N, T, 2, device=dev)
     ga = torch.randn(N, T, S, device=dev) * 0.01; gb = torch.randn(N, T, S, device=dev)
-    gp = torch.empty_like(p); ge = torch.empty_like(e)
+    gp = torch.empty(N, T, ld, device=dev, dtype=dt); ge = torch.empty_like(gp)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def fwd():
-        rc = lib.simulst_mma_train_fwd(p.data_ptr(), 1, e.data_ptr(), 1, None, alpha.data_ptr(), beta.data_ptr(),
-                                       side.data_ptr(), N, T, S, 1e-6, 0, 3, status.data_ptr(), st)
+        rc = lib.simulst_mma_train_fwd_pitched(p.data_ptr(), 1, S, e.data_ptr(), 1, S, None, alpha.data_ptr(), ld,
+                                               beta.data_ptr(), ld, side.data_ptr(), None, N, T, S, 1e-6, 0, 3,
+                                               status.data_ptr(), st)
         assert rc == 0, rc
 
     def bwd():
-        rc = lib.simulst_mma_train_bwd(p.data_ptr(), 1, e.data_ptr(), 1, None, alpha.data_ptr(), side.data_ptr(),
-                                       ga.data_ptr(), gb.data_ptr(), gp.data_ptr(), 1, ge.data_ptr(), 1,
-                                       N, T, S, 1e-6, 0, 3, st)
+        rc = lib.simulst_mma_train_bwd_pitched(p.data_ptr(), 1, S, e.data_ptr(), 1, S, None, alpha.data_ptr(), ld,
+                                               side.data_ptr(), ga.data_ptr(), S, gb.data_ptr(), S, None,
+                                               gp.data_ptr(), 1, ld, ge.data_ptr(), 1, ld, N, T, S, 1e-6, 0, 3, st)
         assert rc == 0, rc
 
     fwd(); bwd(); torch.cuda.synchronize()
     f, b = timeit(fwd), timeit(bwd)
     el = N * T * S
     print(json.dumps({"op": "mma_fwd_bwd", "rows": N, "tgt": T, "src": S, "dtype_in": "bf16",
-                      "fwd_us": round(f, 1), "bwd_us": round(b, 1),
+                      "out_pitch": ld, "fwd_us": round(f, 1), "bwd_us": round(b, 1),
                       "elements_per_s": el / (f + b) * 1e6,
                       "fwd_gbs": round(el * 12 / f / 1e3, 1), "bwd_gbs": round(el * 20 / b / 1e3, 1),
                       "fwd_bwd_gbs": round(el * 32 / (f + b) / 1e3, 1),
@@ -106,9 +110,9 @@ def cif_point(B, S, C=256):
 if __name__ == "__main__":
     SRC = [int(v) for v in os.environ["SRC"].split(",")] if os.environ.get("SRC") else (512, 1024, 2048, 4096, 6000)
     for S in SRC:
-        for T in (64, 128, 256, 512):
+        for T in ([int(v) for v in os.environ["TGT"].split(",")] if os.environ.get("TGT") else (64, 128, 256, 512)):
             mma_point(ROWS, T, S)
             torch.cuda.empty_cache()
-    for S in (512, 1024, 1500, 2048, 4096, 6000):
+    for S in (() if os.environ.get("NO_CIF") else (512, 1024, 1500, 2048, 4096, 6000)):
         cif_point(64, S)
         torch.cuda.empty_cache()
