@@ -496,7 +496,8 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     const bool fixer = MASKED && row_len > 0 && last_col >= j0 && last_col < j0 + VPT;     // owner of the last live column
     (void)fixer;
     if constexpr (MASKED) {
-        if (row_len == 0) {
+        // (a barrier reduction: the compiler then knows the exit is taken by the whole CTA or by nobody)
+        if (__syncthreads_or(row_len == 0 ? 1 : 0)) {
             // no live column: every gradient of the row is zero
             float zero_v[VPT];
 #pragma unroll

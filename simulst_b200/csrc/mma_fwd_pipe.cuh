@@ -235,7 +235,10 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
         }
     }
     if constexpr (FULL && MASKED) {
-        if (last < 0) {
+        // (a barrier reduction: the compiler then knows the exit is taken by the whole CTA or by nobody;
+        //  a plain data-dependent return makes it treat the rest of the kernel as divergent code and give
+        //  up the uniform datapath)
+        if (__syncthreads_or(last < 0 ? 1 : 0)) {
             // no live column: alpha = beta = 0 for the whole row (no mass-preservation column exists)
             float2 z2[H];
 #pragma unroll
