@@ -65,7 +65,7 @@ static bool split_masked_call(const MmaParams& prm, int mode, const Config& cfg,
     if (prm.flags & (SIMULST_MMA_LEFT_PADDING | SIMULST_MMA_RIGHT_PADDING)) return false;
     if (cfg.threads > 512 || cfg.vpt > 12) return false;
     if (prm.shift) return true;
-    if (!prm.tma || !prm.vec_out || prm.S % cfg.vpt != 0) return false;
+    if (!prm.tma || !prm.vec_out || prm.S % cfg.vpt != 0 || prm.pitched) return false;
     return true;
 }
 
@@ -263,8 +263,9 @@ int mma_fwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
     // Dense kernels with shifted staging (SHIFT instantiations): input rows that are not 16-byte multiples
     // and / or S not a multiple of the per-thread element count, when the OUTPUT rows are 16-byte pitched
     // with room for whole threads.  The CTA then keeps 16 spare columns.
+    prm.pitched = prm.ld_p != S || prm.ld_e != S || prm.ld_alpha != S || prm.ld_beta != S;
     if (use_tma && pool_ratio == 0 && prm.pipe && mode != kModeSoftCk && alpha != nullptr && S + 16 <= 6144 &&
-        (!prm.tma || S % cfg.vpt != 0) && !(flags & SIMULST_MMA_LEFT_PADDING)) {
+        (!prm.tma || S % cfg.vpt != 0 || prm.pitched) && !(flags & SIMULST_MMA_LEFT_PADDING)) {
         const Config c2 = pick_config(S + 16);
         const int need = round_up(S, c2.vpt);
         if (c2.threads <= 512 && c2.vpt <= 12 && (c2.vpt < 12 || S + 32 <= 6144) && prm.vec_out && prm.ld_alpha >= need &&
@@ -419,8 +420,10 @@ int mma_bwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
     Config cfg = pick_config(S);
     const int mode = mode_of(flags, chunk_size);
     // dense kernel with shifted staging: see mma_fwd_core
+    prm.pitched = prm.ld_p != S || prm.ld_e != S || prm.ld_alpha != S || prm.ld_ga != S || prm.ld_gb != S ||
+                  prm.ld_gp != S || prm.ld_ge != S;
     if (use_tma && pool_ratio == 0 && prm.fast && mode != kModeSoftCk && alpha != nullptr && S + 16 <= 6144 &&
-        (!prm.tma || S % cfg.vpt != 0) && !(flags & SIMULST_MMA_LEFT_PADDING)) {
+        (!prm.tma || S % cfg.vpt != 0 || prm.pitched) && !(flags & SIMULST_MMA_LEFT_PADDING)) {
         const Config c2 = pick_config(S + 16);
         const int need = round_up(S, c2.vpt);
         if (c2.threads <= 512 && c2.vpt <= 12 && (c2.vpt < 12 || S + 32 <= 6144) && out16 && prm.ld_gp >= need &&
@@ -492,6 +495,7 @@ extern "C" {
 int simulst_mma_out_pitch(int S) {
     if (S <= 0 || S > SIMULST_MMA_MAX_SRC) return SIMULST_E_SHAPE;
     const Config c1 = pick_config(S);
+    if (S % 8 == 0 && S % c1.vpt == 0) return S;      // dense rows already qualify, whatever the dtype
     if (S + 16 > 6144) return round_up(S, c1.vpt > 8 ? c1.vpt : 8);
     const Config c2 = pick_config(S + 16);
     // a multiple of 8 elements (16-byte rows for every dtype) that holds whole threads of either configuration

@@ -418,8 +418,11 @@ mma_bwd_fast_kernel(const MmaParams prm) {
     const bool in_row = !RAGGED || j0 < S;              // this thread's VPT columns exist
 
     // row pitches in elements; the batch stride of a tensor is T * pitch
-    const int ld_p = prm.ld_p, ld_e = prm.ld_e, ld_a = prm.ld_alpha, ld_ga = prm.ld_ga, ld_gb = prm.ld_gb,
-              ld_gp = prm.ld_gp, ld_ge = prm.ld_ge;
+    // (only the SHIFT instantiation takes pitched tensors; everywhere else the pitch is S, which lets the
+    //  compiler share one row offset between all tensors and keep it in the uniform datapath)
+    const int ld_p = SHIFT ? prm.ld_p : S, ld_e = SHIFT ? prm.ld_e : S, ld_a = SHIFT ? prm.ld_alpha : S,
+              ld_ga = SHIFT ? prm.ld_ga : S, ld_gb = SHIFT ? prm.ld_gb : S, ld_gp = SHIFT ? prm.ld_gp : S,
+              ld_ge = SHIFT ? prm.ld_ge : S;
     const size_t nt = (size_t)n * T_len;
     const T* p_in = reinterpret_cast<const T*>(prm.p) + nt * ld_p;
     const T* e_in = SOFT ? reinterpret_cast<const T*>(prm.e) + nt * ld_e : nullptr;
@@ -633,34 +636,24 @@ mma_bwd_fast_kernel(const MmaParams prm) {
             lds_row2<float, VPT>(row, j0, v);
         }
     };
-    // MASKED: the fixer neutralises the copy overhang [L, end of the last 16-byte granule) of a landed row
-    auto fix_bytes = [&](unsigned char* slot, unsigned sh, unsigned esz, unsigned pattern) {
-        const unsigned live_end = sh + (unsigned)row_len * esz;
-        const unsigned dirt_end = (live_end + 15u) & ~15u;
-        for (unsigned o = live_end; o < dirt_end; o += esz) {
-            if (esz == 4u) *reinterpret_cast<unsigned*>(slot + o) = pattern;
-            else *reinterpret_cast<unsigned short*>(slot + o) = (unsigned short)pattern;
-        }
-        if constexpr (SHIFT) {
-            // the previous row in this slot may have started up to 15 bytes later and reached one granule further
-            if (dirt_end + 16u <= (unsigned)(THREADS * VPT) * esz) {
-                const unsigned w = esz == 4u ? pattern : (pattern | (pattern << 16));
-                *reinterpret_cast<uint4*>(slot + dirt_end) = make_uint4(w, w, w, w);
-            }
-        }
+    // MASKED: the fixer neutralises the copy overhang behind the row's end in a landed row
+    auto fix_t = [&](unsigned char* slot, unsigned sh, unsigned pattern) {
+        fix_overhang<(int)sizeof(T), SHIFT>(slot, sh + (unsigned)row_len * (unsigned)sizeof(T), pattern,
+                                            (unsigned)(THREADS * VPT * sizeof(T)));
+    };
+    auto fix_f = [&](unsigned char* slot, unsigned sh) {
+        fix_overhang<4, SHIFT>(slot, sh + (unsigned)row_len * 4u, 0u, (unsigned)(THREADS * VPT * 4));
     };
     // all rows that arrive with producer iteration q (step i = T-1-q)
     auto fix_stage = [&](int q) {
         const int i = T_len - 1 - q;
         unsigned char* st = stage0 + (q % NS) * L::kStage;
-        constexpr unsigned kNegInf = std::is_same<T, float>::value ? 0xff800000u
-                                   : (std::is_same<T, __nv_bfloat16>::value ? 0xff80u : 0xfc00u);
-        fix_bytes(st + L::kOffP, SHIFT ? sh_of(p_lo, i, p_pitch) : 0u, (unsigned)sizeof(T), 0u);
-        if (SOFT) fix_bytes(st + L::kOffE, SHIFT ? sh_of(e_lo, i, e_pitch) : 0u, (unsigned)sizeof(T), kNegInf);
-        if (has_ga) fix_bytes(st + L::kOffGA, SHIFT ? sh_of(ga_lo, i, ga_pitch) : 0u, 4u, 0u);
-        if (has_gb) fix_bytes(st + L::kOffGB, SHIFT ? sh_of(gb_lo, i, gb_pitch) : 0u, 4u, 0u);
-        if (i > 0) fix_bytes(alpha0 + (q % NA) * L::kFRow, SHIFT ? sh_of(al_lo, i - 1, al_pitch) : 0u, 4u, 0u);
-        if (SOFT && q == 0) fix_bytes(alpha0 + (NA - 1) * L::kFRow, SHIFT ? sh_of(al_lo, i, al_pitch) : 0u, 4u, 0u);
+        fix_t(st + L::kOffP, SHIFT ? sh_of(p_lo, i, p_pitch) : 0u, 0u);
+        if (SOFT) fix_t(st + L::kOffE, SHIFT ? sh_of(e_lo, i, e_pitch) : 0u, neg_inf_bits<T>());
+        if (has_ga) fix_f(st + L::kOffGA, SHIFT ? sh_of(ga_lo, i, ga_pitch) : 0u);
+        if (has_gb) fix_f(st + L::kOffGB, SHIFT ? sh_of(gb_lo, i, gb_pitch) : 0u);
+        if (i > 0) fix_f(alpha0 + (q % NA) * L::kFRow, SHIFT ? sh_of(al_lo, i - 1, al_pitch) : 0u);
+        if (SOFT && q == 0) fix_f(alpha0 + (NA - 1) * L::kFRow, SHIFT ? sh_of(al_lo, i, al_pitch) : 0u);
     };
     // max over this thread's live columns of a staged energy row (row index i_row)
     auto row_max = [&](const void* row, int i_row) -> float {
@@ -1158,7 +1151,7 @@ int launch_mma_bwd_fast(const MmaParams& prm, cudaStream_t stream) {
         if (prm.shift && prm.S + 16 <= CAP && !(prm.flags & SIMULST_MMA_LEFT_PADDING) &&
             (prm.mask == nullptr || (prm.flags & SIMULST_MMA_RIGHT_PADDING)))
             return launch_mma_bwd_fast_impl<THREADS, VPT, T, SOFT, true, true, true, true>(prm, stream);
-        if (!prm.vec_out || !prm.tma) return 1;
+        if (!prm.vec_out || !prm.tma || prm.pitched) return 1;
         if (prm.S > CAP || prm.S % VPT != 0) return 1;
         if (prm.mask != nullptr) {
             // masked rows: only when the caller promises a right-padding mask

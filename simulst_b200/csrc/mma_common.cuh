@@ -41,6 +41,8 @@ struct MmaParams {
                             // (j >= len), 2 only the other rows -- the two passes of a masked call
     // Row pitches in ELEMENTS of each [N,T,S] tensor (the batch stride is T * pitch); S when dense.
     int ld_p, ld_e, ld_alpha, ld_beta, ld_ga, ld_gb, ld_gp, ld_ge;
+    int pitched;            // 1: some row pitch differs from S (only the SHIFT instantiations of the dense kernels
+                            // and the generic kernels honour pitches; the other dense instantiations index with S)
     int shift;              // 1: dense kernels may take the row although its inputs are not 16-byte multiples
                             // and / or S is not a multiple of the per-thread element count (SHIFT
                             // instantiations: aligned-superset bulk copies, reads at the row's byte offset,
@@ -179,6 +181,34 @@ __device__ __forceinline__ void lds_row2_sh(const void* __restrict__ slot, unsig
         }
     }
 }
+// MASKED rows: neutralise the copy overhang [live_end, end of its 16-byte granule) of a staged row (byte
+// offsets inside the ring slot; `pattern` holds the neutral element in its low ESZ bytes).  Unrolled,
+// predicated, independent stores: a counted loop costs one branch latency per element on the one warp
+// every other warp waits for.  WIDE (SHIFT rows): also the following granule, which the previous row
+// of this slot may have reached (rows start at varying byte offsets), when it lies inside the slot.
+template <int ESZ, bool WIDE>
+__device__ __forceinline__ void fix_overhang(unsigned char* slot, unsigned live_end, unsigned pattern, unsigned slot_bytes) {
+    const unsigned dirt_end = (live_end + 15u) & ~15u;
+#pragma unroll
+    for (int k = 0; k < 16 / ESZ - 1; ++k) {
+        const unsigned o = live_end + (unsigned)(k * ESZ);
+        if (o < dirt_end) {
+            if constexpr (ESZ == 4) *reinterpret_cast<unsigned*>(slot + o) = pattern;
+            else *reinterpret_cast<unsigned short*>(slot + o) = (unsigned short)pattern;
+        }
+    }
+    if constexpr (WIDE) {
+        if (dirt_end + 16u <= slot_bytes) {
+            const unsigned w = ESZ == 4 ? pattern : (pattern | (pattern << 16));
+            *reinterpret_cast<uint4*>(slot + dirt_end) = make_uint4(w, w, w, w);
+        }
+    }
+}
+template <typename T>
+__host__ __device__ constexpr unsigned neg_inf_bits() {
+    return std::is_same<T, float>::value ? 0xff800000u : (std::is_same<T, __nv_bfloat16>::value ? 0xff80u : 0xfc00u);
+}
+
 // Element k (a run-time index, 0 <= k < VPT) of a register-resident pair array: a select tree on the bits
 // of k (VPT - 1 selects) instead of VPT compare + select pairs.
 template <int VPT>

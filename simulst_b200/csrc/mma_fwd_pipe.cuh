@@ -119,7 +119,10 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
     const bool vec_out = FULL || prm.vec_out != 0;
     constexpr int NS = PS::kNS;
 
-    const int ld_p = prm.ld_p, ld_e = prm.ld_e, ld_a = prm.ld_alpha, ld_b = prm.ld_beta;
+    // row pitches: only the SHIFT instantiation takes pitched tensors; everywhere else the pitch is S, which
+    // lets the compiler share one row offset between the four tensors
+    const int ld_p = SHIFT ? prm.ld_p : S, ld_e = SHIFT ? prm.ld_e : S, ld_a = SHIFT ? prm.ld_alpha : S,
+              ld_b = SHIFT ? prm.ld_beta : S;
     const T* gp = reinterpret_cast<const T*>(prm.p) + (size_t)n * T_len * ld_p;
     const T* ge = SOFT ? reinterpret_cast<const T*>(prm.e) + (size_t)n * T_len * ld_e : nullptr;
     float* g_alpha = prm.alpha + (size_t)n * T_len * ld_a;
@@ -306,22 +309,10 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
             lds_row2_sh<T, VPT>(slot, sh, j0, THREADS * VPT * (int)sizeof(T), v);
         }
     };
-    // MASKED: the fixer neutralises the copy overhang [L, end of the last 16-byte granule) of a landed row
-    auto fix_row = [&](T* slot, unsigned sh, float fillv) {
-        const unsigned live_end = sh + (unsigned)L_row * (unsigned)sizeof(T);
-        const unsigned dirt_end = (live_end + 15u) & ~15u;
-        unsigned char* b = reinterpret_cast<unsigned char*>(slot);
-        const T nv = from_f32<T>(fillv);
-        for (unsigned o = live_end; o < dirt_end; o += (unsigned)sizeof(T)) *reinterpret_cast<T*>(b + o) = nv;
-        if constexpr (SHIFT) {
-            // the previous row in this slot may have started up to 15 bytes later and reached one granule further
-            if (dirt_end + 16u <= (unsigned)(THREADS * VPT * sizeof(T))) {
-                Pack<T, 16 / (int)sizeof(T)> pk;
-#pragma unroll
-                for (int k = 0; k < 16 / (int)sizeof(T); ++k) pk.v[k] = nv;
-                *reinterpret_cast<Pack<T, 16 / (int)sizeof(T)>*>(b + dirt_end) = pk;
-            }
-        }
+    // MASKED: the fixer neutralises the copy overhang behind the row's end in a landed row
+    auto fix_row = [&](T* slot, unsigned sh, unsigned pattern) {
+        fix_overhang<(int)sizeof(T), SHIFT>(reinterpret_cast<unsigned char*>(slot), sh + (unsigned)L_row * (unsigned)sizeof(T),
+                                            pattern, (unsigned)(THREADS * VPT * sizeof(T)));
     };
     const float eps_x = (MASKED && nl == 0) ? 0.f : eps;    // no eps from the columns of a thread beyond the row
     unsigned umax32 = 0u;                   // SHIFT: first-level prob_check on the fp32 bit patterns
@@ -372,8 +363,8 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
             if (slotM == NS) { slotM = 0; parM ^= 1u; }
             mbar_wait(&bars[slotM], parM);
             if (MASKED && fixer) {
-                fix_row(stage_p(slotM), SHIFT ? sh_of(p_lo, it + 2, p_pitch) : 0u, 0.f);
-                fix_row(stage_e(slotM), SHIFT ? sh_of(e_lo, it + 2, e_pitch) : 0u, -INFINITY);
+                fix_row(stage_p(slotM), SHIFT ? sh_of(p_lo, it + 2, p_pitch) : 0u, 0u);
+                fix_row(stage_e(slotM), SHIFT ? sh_of(e_lo, it + 2, e_pitch) : 0u, neg_inf_bits<T>());
             }
             if constexpr (SHIFT) {
                 float2 Em[H];
@@ -416,7 +407,7 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
             unsigned parM = parI;
             if (slotM == NS) { slotM = 0; parM ^= 1u; }
             mbar_wait(&bars[slotM], parM);
-            fix_row(stage_p(slotM), SHIFT ? sh_of(p_lo, it + 2, p_pitch) : 0u, 0.f);
+            fix_row(stage_p(slotM), SHIFT ? sh_of(p_lo, it + 2, p_pitch) : 0u, 0u);
         }
         // ---- INV(it+1): local chains
         float2 p_n[H], cpre[H], Dl[H];
@@ -676,7 +667,7 @@ int launch_mma_fwd_pipe(const MmaParams& prm, cudaStream_t stream) {
     if (prm.shift && prm.S + 16 <= THREADS * VPT && !(prm.flags & SIMULST_MMA_LEFT_PADDING) &&
         (prm.mask == nullptr || (prm.flags & SIMULST_MMA_RIGHT_PADDING)))
         return launch_mma_fwd_pipe_impl<THREADS, VPT, T, SOFT, true, true, true, true, true>(prm, stream);
-    if (!prm.tma) return 1;
+    if (!prm.tma || prm.pitched) return 1;
     // right-padded rows (caller's promise): dense path with a per-row live length
     if (prm.mask != nullptr && (prm.flags & SIMULST_MMA_RIGHT_PADDING) && !(prm.flags & SIMULST_MMA_LEFT_PADDING) &&
         prm.vec_out && prm.S % VPT == 0 && prm.S <= THREADS * VPT)
