@@ -511,6 +511,10 @@ def run_ours(args):
                                                 "elements counted over the full [N,T,S] grid", **res}
         except Exception as exc:  # pragma: no cover
             extras["masked_batch"] = {"error": repr(exc)}
+        try:
+            extras["unaligned_rows"] = bench_unaligned(lib, dev)
+        except Exception as exc:  # pragma: no cover
+            extras["unaligned_rows"] = {"error": repr(exc)}
         extras.update(side_benchmarks(lib, dev))
         best, mean, sec, cores = time_cpu(reps=2, warmup=1)
         cpu_base = {"value": mean, "unit": UNIT, "cores": cores, "kind": _reference_functions()[0],
@@ -865,6 +869,58 @@ def step_cpu_baseline(p, se):
                 "sample": "same 1024 rows x src 1024, 5 consecutive steps after 1 warm-up, best"}
     except Exception as exc:  # pragma: no cover
         return {"error": repr(exc)}
+
+
+def bench_unaligned(lib, dev):
+    """Source lengths whose rows are not 16-byte multiples (S = 1500 in bf16 is the CIF config's own S; S = 999
+    has rows at 2-byte offsets), 512 rows x 128 steps, fwd + bwd through the row-pitch entry points: outputs with
+    the pitch simulst_mma_out_pitch(S) asks for (what the Python wrapper allocates; dense kernels with shifted
+    staging), the same call with dense outputs (generic kernels), and the aligned neighbour S = 1504 / 1000."""
+    import torch
+    from simulst_b200 import _lib
+    st = torch.cuda.current_stream(dev).cuda_stream
+    n, t = N_ROWS, T
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    out = {"config": f"{n} rows x tgt {t}, bf16 in, L2 flushed before every launch, median of 5",
+           "algorithmic_bytes_per_element": 32}
+    peak, _ = measured_peak()
+    g = torch.Generator().manual_seed(77)
+    for s_len, pitched in ((1500, True), (1500, False), (1504, True), (999, True), (999, False), (1000, True)):
+        ld = int(lib.simulst_mma_out_pitch(s_len)) if pitched else s_len
+        p = torch.sigmoid(torch.randn(n, t, s_len, generator=g) - 2).to(dev, torch.bfloat16)
+        e = torch.randn(n, t, s_len, generator=g).to(dev, torch.bfloat16)
+        alpha = torch.empty(n, t, ld, device=dev)
+        beta = torch.empty_like(alpha)
+        side = torch.empty(n, t, 2, device=dev)
+        ga = torch.randn(n, t, s_len, device=dev) * 0.01
+        gb = torch.randn(n, t, s_len, device=dev)
+        gp = torch.empty(n, t, ld, device=dev, dtype=torch.bfloat16)
+        ge = torch.empty_like(gp)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        fl = _lib.MMA_SOFT | _lib.MMA_MASS_PRESERVATION
+
+        def fwd():
+            _lib.check(lib.simulst_mma_train_fwd_pitched(
+                p.data_ptr(), _lib.BF16, s_len, e.data_ptr(), _lib.BF16, s_len, None, alpha.data_ptr(), ld,
+                beta.data_ptr(), ld, side.data_ptr(), None, n, t, s_len, EPS, 0, fl, status.data_ptr(), st),
+                "simulst_mma_train_fwd_pitched")
+
+        def bwd():
+            _lib.check(lib.simulst_mma_train_bwd_pitched(
+                p.data_ptr(), _lib.BF16, s_len, e.data_ptr(), _lib.BF16, s_len, None, alpha.data_ptr(), ld,
+                side.data_ptr(), ga.data_ptr(), s_len, gb.data_ptr(), s_len, None, gp.data_ptr(), _lib.BF16, ld,
+                ge.data_ptr(), _lib.BF16, ld, n, t, s_len, EPS, 0, fl, st), "simulst_mma_train_bwd_pitched")
+        fwd()
+        bwd()
+        torch.cuda.synchronize()
+        f_us, b_us = _events_us(fwd, 5, flush), _events_us(bwd, 5, flush)
+        el = n * t * s_len
+        out[f"src{s_len}_" + ("pitch%d" % ld if pitched else "dense_outputs")] = {
+            "fwd_us": f_us, "bwd_us": b_us, "value": el / ((f_us + b_us) * 1e-6), "unit": UNIT,
+            "roofline_frac": el * 32 / ((f_us + b_us) * 1e-6) / 1e9 / peak}
+        del p, e, alpha, beta, ga, gb, gp, ge
+        torch.cuda.empty_cache()
+    return out
 
 
 def bench_config1(lib, dev):
