@@ -490,6 +490,9 @@ mma_bwd_fast_kernel(const MmaParams prm) {
         row_len = 0;
 #pragma unroll
         for (int w = 0; w < NW; ++w) row_len += ci[w];
+        // (through a shuffle: the compiler then knows the value is warp-uniform and keeps the byte counts and
+        //  addresses derived from it in the uniform datapath)
+        row_len = __shfl_sync(kFull, row_len, 0);
     }
     const int nl = MASKED ? max(0, min(VPT, row_len - j0)) : VPT;      // live columns of this thread
     const bool inside = MASKED ? nl > 0 : in_row;

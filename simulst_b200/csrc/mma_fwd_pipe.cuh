@@ -190,6 +190,9 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
     __syncthreads();
     if (SHIFT ? count_live : mp_add) {
         last = (int)combine_sum<NW>(xbuf, lane) - 1;
+        // (through a shuffle: the compiler then knows the value is warp-uniform and keeps the byte counts and
+        //  addresses derived from it in the uniform datapath)
+        if constexpr (MASKED) last = __shfl_sync(kFull, last, 0);
         __syncthreads();
     }
     // element of this thread that sits on the mass-preservation column (-1: none)
