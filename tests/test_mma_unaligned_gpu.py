@@ -227,3 +227,77 @@ def test_broken_promise_on_unaligned_rows_is_flagged():
             simulst_b200.check_status()
     finally:
         simulst_b200.assume_right_padding(False)
+
+
+def _random_cases(count, seed):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    dts = [torch.float32, torch.bfloat16, torch.float16]
+    for q in range(count):
+        s = int(torch.randint(1, 4200, (1,), generator=g))
+        if q % 5 == 0:          # capacities' edges: a row that leaves exactly 16 / 15 spare columns, tiny rows
+            s = [1008, 1009, 2032, 2033, 3, 17, 4080, 4081][(q // 5) % 8]
+        n = int(torch.randint(2, 6, (1,), generator=g))
+        t = int(torch.randint(1, 9, (1,), generator=g))
+        out.append((n, t, s, dts[q % 3], q % 4, bool((q // 2) % 2), bool((q // 3) % 2) or q % 4 == 0))
+    return out
+
+
+@pytest.mark.parametrize("n,t,s,dtype,mask_kind,soft,mp", _random_cases(48, 2024),
+                         ids=lambda v: str(v).replace("torch.", ""))
+def test_random_lengths_and_masks_match_oracle(n, t, s, dtype, mask_kind, soft, mp):
+    """Seeded random source lengths (unaligned rows and rows at the edges of a CTA's capacity), dtypes and
+    modes; mask_kind 0 none, 1 right-padded with random lengths down to 1 (split by row), 2 the same with the
+    right-padding promise, 3 right-padded lengths plus one arbitrary (holey) mask row."""
+    g = torch.Generator().manual_seed(31 * s + n)
+    p, se, _, ga, gb = _seeded(n, t, s, seed=12000 + s)
+    p, se = p.to(dtype), se.to(dtype)
+    mask = None
+    if mask_kind:
+        lens = torch.randint(1, s + 1, (n,), generator=g)
+        lens[0] = s
+        mask = torch.arange(s)[None, :] >= lens[:, None]
+        if mask_kind == 3 and s > 4:
+            mask[-1] = False
+            mask[-1, 1] = True          # a hole: this row takes the arbitrary-mask pass
+    se_in = se if soft else None
+    a_o, b_o, gp_o, ge_o = _oracle(p.float(), se.float() if soft else None, mask, mp, ga, gb)
+    a64, b64, gp64, ge64 = _oracle(p.float(), se.float() if soft else None, mask, mp, ga, gb, torch.float64)
+    simulst_b200.assume_right_padding(mask_kind == 2)
+    try:
+        alpha, beta, gp, ge, _ = _run(p, se_in, mask, mp, ga, gb, dtype)
+        simulst_b200.check_status()
+    finally:
+        simulst_b200.assume_right_padding(False)
+    tag = f"random n{n} T{t} S{s} {str(dtype)[6:]} mask{mask_kind} soft{int(soft)} mp{int(mp)}"
+    assert_parity(alpha, a_o, tag + " alpha", a64)
+    if soft:
+        assert_parity(beta, b_o, tag + " beta", b64)
+    floor = 2.0 * 2.0 ** -24 * s ** 0.5 * max(float(ga.abs().max()), float(gb.abs().max()))
+    rt = 1e-5 if dtype == torch.float32 else 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    assert_parity(gp, gp_o, tag + " grad_p", gp64, rtol=rt, extra_atol=floor)
+    if soft:
+        assert_parity(ge, ge_o, tag + " grad_energy", ge64, rtol=rt, extra_atol=floor)
+
+
+def test_rows_without_live_columns():
+    """A padding mask that leaves a row no live column: alpha, beta and both gradients of that row are zero
+    (the reference would fail on such a row with a scatter index of -1); its neighbours are unaffected."""
+    from simulst_b200 import ops
+    n, t, s = 3, 6, 1500
+    p, se, _, ga, gb = _seeded(n, t, s, seed=77)
+    lens = torch.tensor([s, 0, 733])
+    mask = torch.arange(s)[None, :] >= lens[:, None]
+    for promise in (False, True):
+        simulst_b200.assume_right_padding(promise)
+        try:
+            alpha, beta, gp, ge, _ = _run(p.bfloat16(), se.bfloat16(), mask, True, ga, gb, torch.bfloat16)
+        finally:
+            simulst_b200.assume_right_padding(False)
+        for x in (alpha[1], beta[1], gp[1], ge[1]):
+            assert float(x.abs().max()) == 0.0
+        keep = torch.tensor([0, 2])
+        a_o, b_o, gp_o, ge_o = _oracle(p.bfloat16().float()[keep], se.bfloat16().float()[keep], mask[keep], True,
+                                       ga[keep], gb[keep])
+        assert_parity(alpha[keep], a_o, "empty-row neighbours alpha")
+        assert_parity(beta[keep], b_o, "empty-row neighbours beta")
