@@ -92,6 +92,13 @@ int simulst_mma_set_pipeline(int mode);
  * kernels, every other row through the arbitrary-mask kernels; each CTA classifies its own row,
  * so there is no host read.  0: one pass through the arbitrary-mask kernels. */
 int simulst_mma_set_mask_split(int enable);
+/* Forward of long rows in small batches on thread-block clusters (csrc/mma_fwd_cluster.cuh): 2 / 4 / 8 CTAs
+ * share a row of 1025..8192 frames (no padding mask, dense 16-byte rows) and exchange their scan totals
+ * through distributed shared memory.  1 (default): when the call has at most 74 rows (half the SMs), i.e.
+ * when one CTA per row would leave most of the GPU dark, and more than 2560 frames per row (below that the
+ * cluster-wide exchange costs more than the extra SMs bring); 0: never; 2: whenever the shape qualifies.
+ * Results are bit-identical to the single-CTA kernel's.  Returns 0 or E_ARG. */
+int simulst_mma_set_cluster(int mode);
 /* 1 = CIF forward/backward through the TMA-staged tile kernels when rows are 16-byte aligned
  * and C <= 512 (default), 0 = always the per-warp kernels (same results bit for bit) */
 int simulst_cif_set_tile(int enable);

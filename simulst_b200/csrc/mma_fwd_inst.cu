@@ -2,6 +2,7 @@
 // -DSIMULST_INST_DTYPE=0|1|2 so the three dtypes compile in parallel).
 #include "mma_fwd.cuh"
 #include "mma_fwd_pipe.cuh"
+#include "mma_fwd_cluster.cuh"
 #include "mma_dispatch.h"
 
 namespace simulst {
@@ -18,6 +19,11 @@ using InstT = __half;
 #endif
 
 int INST_NAME(const MmaParams& prm, int mode, int threads, int vpt, cudaStream_t stream) {
+    if (prm.cluster && prm.pipe && mode != kModeSoftCk) {
+        const int rc = mode == kModeHard ? launch_mma_fwd_cluster<InstT, false>(prm, stream)
+                                         : launch_mma_fwd_cluster<InstT, true>(prm, stream);
+        if (rc != 1) return rc;                 /* 1 = the call does not qualify for the cluster kernel */
+    }
 #define X(TH, VP)                                                                         \
     if (threads == TH && vpt == VP) {                                                     \
         if constexpr (TH <= kPipeMaxThreads) {                                            \
