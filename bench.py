@@ -512,6 +512,10 @@ def run_ours(args):
         except Exception as exc:  # pragma: no cover
             extras["masked_batch"] = {"error": repr(exc)}
         try:
+            extras["long_rows_small_batch"] = bench_cluster(lib, dev)
+        except Exception as exc:  # pragma: no cover
+            extras["long_rows_small_batch"] = {"error": repr(exc)}
+        try:
             extras["unaligned_rows"] = bench_unaligned(lib, dev)
         except Exception as exc:  # pragma: no cover
             extras["unaligned_rows"] = {"error": repr(exc)}
@@ -869,6 +873,49 @@ def step_cpu_baseline(p, se):
                 "sample": "same 1024 rows x src 1024, 5 consecutive steps after 1 warm-up, best"}
     except Exception as exc:  # pragma: no cover
         return {"error": repr(exc)}
+
+
+def bench_cluster(lib, dev):
+    """SURVEY's long-form row count (BASELINE config 5: 8 utterances x 8 heads = 64 rows), forward, tgt 128: one CTA
+    per row (84 SMs idle) against one thread-block cluster per row (csrc/mma_fwd_cluster.cuh: the library's choice
+    for <= 74 rows of more than 2560 frames)."""
+    import torch
+    from simulst_b200 import _lib
+    st = torch.cuda.current_stream(dev).cuda_stream
+    n, t = 64, 128
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    peak, _ = measured_peak()
+    out = {"config": f"{n} rows x tgt {t}, bf16 in, forward (alpha + beta), L2 flushed before every launch, median of 7",
+           "algorithmic_bytes_per_element": 12}
+    g = torch.Generator().manual_seed(5)
+    for s_len in (3000, 4096, 6000, 8192):
+        p = torch.sigmoid(torch.randn(n, t, s_len, generator=g) - 2).to(dev, torch.bfloat16)
+        e = torch.randn(n, t, s_len, generator=g).to(dev, torch.bfloat16)
+        alpha = torch.empty(n, t, s_len, device=dev)
+        beta = torch.empty_like(alpha)
+        side = torch.empty(n, t, 2, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        fl = _lib.MMA_SOFT | _lib.MMA_MASS_PRESERVATION
+
+        def fwd():
+            _lib.check(lib.simulst_mma_train_fwd(p.data_ptr(), _lib.BF16, e.data_ptr(), _lib.BF16, None, alpha.data_ptr(),
+                                                 beta.data_ptr(), side.data_ptr(), n, t, s_len, EPS, 0, fl,
+                                                 status.data_ptr(), st), "simulst_mma_train_fwd")
+        res = {}
+        try:
+            for mode, name in ((0, "one_cta_per_row_us"), (1, "cluster_per_row_us")):
+                lib.simulst_mma_set_cluster(mode)
+                fwd()
+                torch.cuda.synchronize()
+                res[name] = _events_us(fwd, 7, flush)
+        finally:
+            lib.simulst_mma_set_cluster(1)
+        res["speedup"] = res["one_cta_per_row_us"] / res["cluster_per_row_us"]
+        res["roofline_frac"] = n * t * s_len * 12 / (res["cluster_per_row_us"] * 1e-6) / 1e9 / peak
+        out[f"src{s_len}"] = res
+        del p, e, alpha, beta
+        torch.cuda.empty_cache()
+    return out
 
 
 def bench_unaligned(lib, dev):
