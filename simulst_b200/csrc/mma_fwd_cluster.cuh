@@ -212,14 +212,13 @@ mma_fwd_cluster_kernel(const MmaParams prm) {
     };
     for (int i = 0; i < NS && i < T_len; ++i) issue(i, i);
 
-    // addresses of this warp's exchange column in every peer, and of the peers' exchange barriers
-    uint32_t peer_x[CL > 1 ? CL - 1 : 1], peer_bar[CL > 1 ? CL - 1 : 1];
-#pragma unroll
-    for (int q = 0; q < CL - 1; ++q) {
-        const unsigned r = (rank + 1u + (unsigned)q) % (unsigned)CL;
-        peer_x[q] = mapa_u32(smem_u32(xbuf + gw * kXW), r);
-        peer_bar[q] = mapa_u32(smem_u32(&xbar[0]), r);
-    }
+    // Lane l < 2 * (CL - 1) of every warp sends one 16-byte half of the warp's eight values to one peer: the
+    // whole exchange of a warp is ONE st.async instruction (one lane per message) instead of 2 * (CL - 1)
+    // single-lane instructions in a row.
+    const bool sender = lane < 2 * (CL - 1);
+    const unsigned peer_rank = (rank + 1u + (unsigned)(lane >> 1)) % (unsigned)CL;
+    const uint32_t peer_x = mapa_u32(smem_u32(xbuf + gw * kXW + (lane & 1) * 4), peer_rank);
+    const uint32_t peer_bar = mapa_u32(smem_u32(&xbar[0]), peer_rank);
 
     const float one_eps = 1.0f + eps;
     float2 a_prev[H];
@@ -317,17 +316,10 @@ mma_fwd_cluster_kernel(const MmaParams prm) {
         // peer, into every other CTA's
         {
             const float x31 = __shfl_sync(kFull, xinc, 31), e31 = __shfl_sync(kFull, einc, 31), u31 = __shfl_sync(kFull, uinc, 31);
-            if (lane == 0) {
-                const float4 lo = make_float4(wm, x31, e31, u31), hi = make_float4(rinc, ws, wd, wr);
-                float4* own = reinterpret_cast<float4*>(xw + gw * kXW);
-                own[0] = lo;
-                own[1] = hi;
-#pragma unroll
-                for (int q = 0; q < CL - 1; ++q) {
-                    st_async_f32x4(peer_x[q] + xoff, lo, peer_bar[q] + (uint32_t)(xb * 8));
-                    st_async_f32x4(peer_x[q] + xoff + 16u, hi, peer_bar[q] + (uint32_t)(xb * 8));
-                }
-            }
+            const float r0 = __shfl_sync(kFull, rinc, 0);
+            const float4 lo = make_float4(wm, x31, e31, u31), hi = make_float4(r0, ws, wd, wr);
+            if (lane < 2) reinterpret_cast<float4*>(xw + gw * kXW)[lane] = lane ? hi : lo;
+            if (sender) st_async_f32x4(peer_x + xoff, (lane & 1) ? hi : lo, peer_bar + (uint32_t)(xb * 8));
         }
         // ---- the exchange: this warp's values are on their way to every CTA; arrive on the own barrier
         // (release: orders this CTA's shared-memory traffic of the iteration like __syncthreads did) and wait
