@@ -22,7 +22,9 @@ int INST_NAME(const MmaParams& prm, int mode, int threads, int vpt, cudaStream_t
     if (prm.cluster && prm.pipe && mode != kModeSoftCk) {
         const int rc = mode == kModeHard ? launch_mma_fwd_cluster<InstT, false>(prm, stream)
                                          : launch_mma_fwd_cluster<InstT, true>(prm, stream);
-        if (rc != 1) return rc;                 /* 1 = the call does not qualify for the cluster kernel */
+        /* 1 = the call does not qualify for the cluster kernel; a launch the device refuses (no cluster
+           scheduling, e.g. under MIG) falls back to one CTA per row as well */
+        if (rc == SIMULST_OK) return rc;
     }
 #define X(TH, VP)                                                                         \
     if (threads == TH && vpt == VP) {                                                     \
