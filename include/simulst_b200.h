@@ -99,6 +99,10 @@ int simulst_mma_set_mask_split(int enable);
  * cluster-wide exchange costs more than the extra SMs bring); 0: never; 2: whenever the shape qualifies.
  * Results are bit-identical to the single-CTA kernel's.  Returns 0 or E_ARG. */
 int simulst_mma_set_cluster(int mode);
+/* Development knob like simulst_mma_set_config: force the cluster shape (CTAs per row: 2 / 4 / 8; threads per
+ * CTA: 96 / 128; eight frames per thread) of the calls that take the cluster kernel; a shape that cannot hold the
+ * row is ignored for that call.  (0, 0) = automatic: slices of at most 1024 frames.  Returns 0 or E_ARG. */
+int simulst_mma_set_cluster_shape(int cl, int threads);
 /* 1 = CIF forward/backward through the TMA-staged tile kernels when rows are 16-byte aligned
  * and C <= 512 (default), 0 = always the per-warp kernels (same results bit for bit) */
 int simulst_cif_set_tile(int enable);

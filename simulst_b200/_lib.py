@@ -41,6 +41,7 @@ SIGNATURES = {
     "simulst_mma_set_pipeline": (c_int, [c_int]),
     "simulst_mma_set_mask_split": (c_int, [c_int]),
     "simulst_mma_set_cluster": (c_int, [c_int]),
+    "simulst_mma_set_cluster_shape": (c_int, [c_int, c_int]),
     "simulst_cif_set_tile_rows": (c_int, [c_int, c_int]),
     "simulst_cif_set_tile": (c_int, [c_int]),
     "simulst_mma_train_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p,

@@ -54,6 +54,7 @@ static int check_device() {
     return c == 1 ? SIMULST_OK : SIMULST_E_ARCH;
 }
 
+static std::atomic<int> g_cluster_shape{0};    // (cl << 16) | threads; 0 = automatic
 static std::atomic<int> g_cluster{1};          // long rows in small batches: 0 never, 1 automatic, 2 whenever the shape qualifies
 static std::atomic<int> g_pooled_grid{1};      // pooled calls: pooled-grid kernels (1) or always expand + dense kernels (0)
 static std::atomic<int> g_split_masked{1};     // masked calls: dense pass for right-padded rows + general pass for the rest
@@ -188,6 +189,13 @@ int simulst_mma_set_tma(int enable) {
     return SIMULST_OK;
 }
 
+int simulst_mma_set_cluster_shape(int cl, int threads) {
+    if (cl == 0 && threads == 0) { g_cluster_shape.store(0, std::memory_order_relaxed); return SIMULST_OK; }
+    if ((cl != 2 && cl != 4 && cl != 8) || (threads != 96 && threads != 128)) return SIMULST_E_ARG;
+    g_cluster_shape.store((cl << 16) | threads, std::memory_order_relaxed);
+    return SIMULST_OK;
+}
+
 int simulst_mma_set_cluster(int mode) {
     if (mode < 0 || mode > 2) return SIMULST_E_ARG;
     g_cluster.store(mode, std::memory_order_relaxed);
@@ -273,6 +281,9 @@ int mma_fwd_core(const void* p_choose, int p_dtype, const void* soft_energy, int
         const int cl_mode = g_cluster.load(std::memory_order_relaxed);
         // (measured at 64 rows x 128 steps, forward: S = 2048 0.88x, 3000 1.09x, 4096 1.11x, 6000 1.69x, 8192 2.26x)
         prm.cluster = pool_ratio == 0 && padding_mask == nullptr && (cl_mode == 2 || (cl_mode == 1 && N <= 74 && S > 2560)) ? 1 : 0;
+        const int shape = g_cluster_shape.load(std::memory_order_relaxed);
+        prm.cluster_cl = shape >> 16;
+        prm.cluster_threads = shape & 0xffff;
     }
     // Dense kernels with shifted staging (SHIFT instantiations): input rows that are not 16-byte multiples
     // and / or S not a multiple of the per-thread element count, when the OUTPUT rows are 16-byte pitched

@@ -42,6 +42,7 @@ struct MmaParams {
     // Row pitches in ELEMENTS of each [N,T,S] tensor (the batch stride is T * pitch); S when dense.
     int ld_p, ld_e, ld_alpha, ld_beta, ld_ga, ld_gb, ld_gp, ld_ge;
     int cluster;            // 1: forward of a long row on a thread-block cluster (few rows: mma_fwd_cluster.cuh)
+    int cluster_cl, cluster_threads;    // forced cluster shape (development knob), 0 = automatic
     int pitched;            // 1: some row pitch differs from S (only the SHIFT instantiations of the dense kernels
                             // and the generic kernels honour pitches; the other dense instantiations index with S)
     int shift;              // 1: dense kernels may take the row although its inputs are not 16-byte multiples

@@ -125,7 +125,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity
 }
 
 template <int THREADS, int VPT, typename T, bool SOFT, int CL>
-__global__ void __launch_bounds__(THREADS, 4)
+__global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 4 : 2))
 mma_fwd_cluster_kernel(const MmaParams prm) {
     using PS = PipeStatic<THREADS, VPT, T, SOFT>;
     constexpr int NW = THREADS / kWarp;
@@ -471,20 +471,29 @@ int launch_mma_fwd_cluster_impl(const MmaParams& prm, cudaStream_t stream) {
     return check_launch();
 }
 
-// Cluster shape for a row of S frames: slices of at most 1024 frames on 96- or 128-thread CTAs.
-// Returns 1 when the call does not qualify (the caller then takes the single-CTA kernels).
+// Cluster shape for a row of S frames: slices of at most 1024 frames (96 or 128 threads per CTA), i.e. 2 / 4 / 8
+// CTAs up to 2048 / 4096 / 8192 frames.  Measured at 64 rows x 128 steps (tests/dev_cluster_probe.py, every shape
+// that holds the row): the time depends on the threads per CTA and on the CTAs per row, hardly on S --
+// 2 CTAs x 96 / 128 / 192 / 256 threads: 131 / 156 / 195 / 210 us; 4 CTAs: 201 / 219 / 257 / 297 us; 8 CTAs x 96 /
+// 128: 244 / 288 us -- and fewer, fatter CTAs never beat the smallest slices that hold the row.
+// prm.cluster_cl / cluster_threads (simulst_mma_set_cluster_shape) force a shape.  Returns 1 when the call does
+// not qualify (the caller then takes the single-CTA kernels).
 template <typename T, bool SOFT>
 int launch_mma_fwd_cluster(const MmaParams& prm, cudaStream_t stream) {
     const int S = prm.S;
     if (prm.mask != nullptr || !prm.tma || !prm.vec_out || prm.pitched || S % 8 != 0 || S <= 1024 || S > 8192) return 1;
-    const int cl = S <= 2048 ? 2 : (S <= 4096 ? 4 : 8);
-    const int per = (S + cl - 1) / cl;                  // 513 .. 1024
-    // every CTA's slice must start on a 16-byte boundary and hold whole threads: slices are 768 or 1024 frames
-    const bool small = per <= 768;
-#define SIMULST_CL(CLV)                                                                                   \
-    if (cl == CLV) return small ? launch_mma_fwd_cluster_impl<96, 8, T, SOFT, CLV>(prm, stream)             \
-                                : launch_mma_fwd_cluster_impl<128, 8, T, SOFT, CLV>(prm, stream);
-    SIMULST_CL(2) SIMULST_CL(4) SIMULST_CL(8)
+    int cl, th;
+    if (prm.cluster_cl != 0) {
+        cl = prm.cluster_cl;
+        th = prm.cluster_threads;
+    } else {
+        cl = S <= 2048 ? 2 : (S <= 4096 ? 4 : 8);
+        th = (S + cl - 1) / cl <= 768 ? 96 : 128;           // frames per CTA: 513 .. 1024
+    }
+    if (cl * th * 8 < S) return 1;
+#define SIMULST_CL(CLV, TH) \
+    if (cl == CLV && th == TH) return launch_mma_fwd_cluster_impl<TH, 8, T, SOFT, CLV>(prm, stream);
+    SIMULST_CL(2, 96) SIMULST_CL(2, 128) SIMULST_CL(4, 96) SIMULST_CL(4, 128) SIMULST_CL(8, 96) SIMULST_CL(8, 128)
 #undef SIMULST_CL
     return 1;
 }

@@ -40,5 +40,14 @@ for S in (1280, 2048, 3000, 4096, 6000, 8192):
             fwd(); torch.cuda.synchronize()
             out[name] = round(timeit(fwd), 1)
         out["speedup"] = round(out["single_cta_us"] / out["cluster_us"], 2)
+        if len(sys.argv) > 2:           # every shape that holds the row
+            for cl in (2, 4, 8):
+                for th in (96, 128):
+                    if cl * th * 8 < S or (cl == 8 and th > 128) or cl * th * 8 >= 2 * S + 2048:
+                        continue
+                    assert lib.simulst_mma_set_cluster_shape(cl, th) == 0
+                    fwd(); torch.cuda.synchronize()
+                    out[f"cl{cl}x{th}"] = round(timeit(fwd), 1)
+            lib.simulst_mma_set_cluster_shape(0, 0)
         print(json.dumps(out), flush=True)
 lib.simulst_mma_set_cluster(1)
