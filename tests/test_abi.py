@@ -65,3 +65,26 @@ def test_multimem_allreduce_rejects_bad_arguments_without_touching_the_device():
     assert lib.simulst_multimem_allreduce_f32(4096, 0, 0, 2, 2, None) == 0
     assert lib.simulst_mma_pooled_workspace_bytes(512, 128, 1024, 8) > 2 * 512 * 128 * 128 * 4
     assert lib.simulst_mma_pooled_workspace_bytes(1, 1, 0, 8) < 0
+
+
+def test_row_pitch_queries_and_argument_checks_without_a_gpu():
+    """simulst_mma_out_pitch is a host-side size query; the row-pitch entry points reject a pitch below S and
+    the cluster knobs reject shapes outside their tables before any CUDA call."""
+    from simulst_b200 import _lib
+    lib = _lib.load()
+    # dense rows that already qualify keep their pitch; everything else gets 16-byte rows with room for whole threads
+    for s, want in ((1024, 1024), (1504, 1504), (8, 8), (4096, 4096), (1500, 1504), (999, 1000), (1001, 1008),
+                    (37, 40), (3001, 3008)):
+        assert lib.simulst_mma_out_pitch(s) == want, s
+    for s in (1, 7, 130, 2047, 4090, 5003, 6100, 6143, 9000, 16384):
+        ld = lib.simulst_mma_out_pitch(s)
+        assert ld >= s and ld % 8 == 0 and ld - s < 32, (s, ld)
+    assert lib.simulst_mma_out_pitch(0) < 0 and lib.simulst_mma_out_pitch(16385) < 0
+    dummy = 256     # a non-null, 256-byte aligned "pointer": the calls below return before touching it
+    assert lib.simulst_mma_train_fwd_pitched(dummy, 1, 99, dummy, 1, 100, None, dummy, 104, dummy, 104, None, None,
+                                             2, 3, 100, 1e-6, 0, 3, None, None) == -2      # ld_p < S
+    assert lib.simulst_mma_train_bwd_pitched(dummy, 1, 100, dummy, 1, 100, None, dummy, 104, None, dummy, 100, dummy,
+                                             100, None, dummy, 1, 96, dummy, 1, 104, 2, 3, 100, 1e-6, 0, 2, None) == -2
+    assert lib.simulst_mma_set_cluster(3) == -1 and lib.simulst_mma_set_cluster(1) == 0
+    assert lib.simulst_mma_set_cluster_shape(3, 128) == -1 and lib.simulst_mma_set_cluster_shape(4, 160) == -1
+    assert lib.simulst_mma_set_cluster_shape(0, 0) == 0
