@@ -714,6 +714,11 @@ mma_bwd_fast_kernel(const MmaParams prm) {
 
     int s = 0, a_slot = 0;
     unsigned parity = 0u;
+    // MASKED: this thread's gradient addresses as running pointers (row i, walking down): with the row index
+    // multiplied out at every store the compiler rebuilt the 64-bit row address from %ctaid each step
+    T* pgp_run = MASKED ? gp_out + (size_t)(T_len - 1) * ld_gp + j0 : nullptr;
+    T* pge_run = (MASKED && SOFT) ? ge_out + (size_t)(T_len - 1) * ld_ge + j0 : nullptr;
+    (void)pgp_run; (void)pge_run;
 #pragma unroll 1
     for (int qi = 0; qi < T_len; ++qi) {
         const int i = T_len - 1 - qi;
@@ -1098,10 +1103,15 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                 const float2 o = fma2(mul2(gL, rx[q]), neg1, mul2(gPk[q], cp[q]));
                 outp[2 * q] = o.x; outp[2 * q + 1] = o.y;
             }
-            if (MASKED ? nl > 0 : inside) st_row_t<T, VPT, true>(gp_out + (size_t)i * ld_gp, j0, S, true, outp);
-            if (MASKED && nl > 0 && nl < VPT) {
-                // the thread the row ends in: zeros over its columns beyond the row
-                for (int k = nl; k < VPT; ++k) gp_out[(size_t)i * ld_gp + j0 + k] = from_f32<T>(0.f);
+            if constexpr (MASKED) {
+                if (nl > 0) st_row_t<T, VPT, true>(pgp_run, 0, S, true, outp);
+                if (nl > 0 && nl < VPT) {
+                    // the thread the row ends in: zeros over its columns beyond the row
+                    for (int k = nl; k < VPT; ++k) pgp_run[k] = from_f32<T>(0.f);
+                }
+                pgp_run -= ld_gp;
+            } else {
+                if (inside) st_row_t<T, VPT, true>(gp_out + (size_t)i * ld_gp, j0, S, true, outp);
             }
         }
         if (SOFT) {
@@ -1115,7 +1125,12 @@ mma_bwd_fast_kernel(const MmaParams prm) {
                     if (k == k_hit) oute[k] -= gEall;
             }
             // (columns beyond the row: exp(-inf - m) = 0 makes their energy gradient an exact zero)
-            if (MASKED ? nl > 0 : inside) st_row_t<T, VPT, true>(ge_out + (size_t)i * ld_ge, j0, S, true, oute);
+            if constexpr (MASKED) {
+                if (nl > 0) st_row_t<T, VPT, true>(pge_run, 0, S, true, oute);
+                pge_run -= ld_ge;
+            } else {
+                if (inside) st_row_t<T, VPT, true>(ge_out + (size_t)i * ld_ge, j0, S, true, oute);
+            }
         }
         side_sum = side_sum_next;
         side_prev_last = side_prev_next;

@@ -345,6 +345,12 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
     int slotI = NS - 1;
     unsigned parI = 1u;
     int sb_w = kExStash - 1;                // exp-stash buffer of step it+1 (INV writes it); RECR(it-1) reads the next one
+    // MASKED: this thread's output addresses as running pointers (row `it` of alpha, row `it - 1` of beta).  With
+    // the row index multiplied out at every store the compiler rebuilt the 64-bit row address from %ctaid each
+    // step (~24 integer multiply-adds per step in these register-tight instantiations).
+    float* pa_run = MASKED ? g_alpha - 2 * (ptrdiff_t)ld_a + j0 : nullptr;
+    float* pb_run = (MASKED && SOFT) ? g_beta - 3 * (ptrdiff_t)ld_b + j0 : nullptr;
+    (void)pa_run; (void)pb_run;
 
     auto body = [&](auto steady_c, const int it) __attribute__((always_inline)) {
         constexpr bool STEADY = decltype(steady_c)::value;
@@ -526,11 +532,15 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
                     for (int k = 0; k < VPT; ++k)
                         if (!is_live(k)) SIMULST_EL(b, k) = 0.f;
                 }
-                if (inside) st_row2_f32<VPT, FULL>(g_beta + (size_t)i * ld_b, j0, S, vec_out, b);
-                if (MASKED && nl > 0 && nl < VPT) {
-                    // the thread the row ends in: its columns beyond the row hold eps * R, not zero (threads
-                    // wholly beyond the row compute exact zeros: their eps is zero) -- overwrite them
-                    for (int k = nl; k < VPT; ++k) g_beta[(size_t)i * ld_b + j0 + k] = 0.f;
+                if constexpr (MASKED) {
+                    if (inside) st_row2_f32<VPT, FULL>(pb_run, 0, S, vec_out, b);
+                    if (nl > 0 && nl < VPT) {
+                        // the thread the row ends in: its columns beyond the row hold eps * R, not zero (threads
+                        // wholly beyond the row compute exact zeros: their eps is zero) -- overwrite them
+                        for (int k = nl; k < VPT; ++k) pb_run[k] = 0.f;
+                    }
+                } else {
+                    if (inside) st_row2_f32<VPT, FULL>(g_beta + (size_t)i * ld_b, j0, S, vec_out, b);
                 }
             }
             if (want_d) {
@@ -554,7 +564,11 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
             finish_u_prefix<VPT>(ubase, sl, P, sfull, z);
 #pragma unroll
             for (int q = 0; q < H; ++q) a_prev[q] = min2(z[q], 1.0f);      // z >= 0: P >= 0, s >= 0
-            if (inside) st_row2_f32<VPT, FULL>(g_alpha + (size_t)it * ld_a, j0, S, vec_out, a_prev);
+            if constexpr (MASKED) {
+                if (inside) st_row2_f32<VPT, FULL>(pa_run, 0, S, vec_out, a_prev);
+            } else {
+                if (inside) st_row2_f32<VPT, FULL>(g_alpha + (size_t)it * ld_a, j0, S, vec_out, a_prev);
+            }
             if (mp || SOFT || want_d) {
                 // alpha entering the row sum / the soft-attention numerator: the mass-preservation
                 // column is left out when it is REPLACED (its residual is added analytically)
@@ -611,6 +625,10 @@ mma_fwd_pipe_kernel(const MmaParams prm) {
             }
         }
         if (++sb_w == kExStash) sb_w = 0;
+        if constexpr (MASKED) {
+            pa_run += ld_a;
+            if (SOFT) pb_run += ld_b;
+        }
     };
 
     using Steady = std::integral_constant<bool, true>;
